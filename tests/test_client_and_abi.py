@@ -1,0 +1,110 @@
+"""CPU-side checks of the product: the client library against the oracle (two independent implementations of the same
+key/noise specification must agree bit for bit), the host-side noise bookkeeping, and the C ABI surface."""
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(tac):
+    header = open(os.path.join(ROOT, "include", "tfhe_aes_cuda.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = sorted(set(re.findall(r"\b(tac_[a-z0-9_]+)\s*\(", header)))
+    assert len(declared) >= 40
+    nm = subprocess.check_output(["nm", "-D", "--defined-only", tac.library_path()], text=True)
+    exported = set(re.findall(r"\bT (tac_[a-z0-9_]+)", nm))
+    missing = [s for s in declared if s not in exported]
+    assert not missing, f"declared in include/tfhe_aes_cuda.h but not exported: {missing}"
+    # the Python binding covers the whole header too
+    assert sorted(tac._SIGNATURES) == declared
+    tac.load_library()
+
+
+def test_library_has_sm100a_kernels(tac):
+    out = subprocess.run(["cuobjdump", "-lelf", tac.library_path()], capture_output=True, text=True)
+    if out.returncode != 0:
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in out.stdout
+
+
+def test_presets_match_reference(tac, ol):
+    # reference parameters.rs:29-61, :77-109, :125-157, :173-205
+    want = {1: (671, 2, 1024, 2, 15, 4, 3, 1, 10, 1, 24, 1), 4: (679, 2, 1024, 2, 15, 4, 3, 1, 11, 2, 16, 4),
+            64: (677, 4, 512, 3, 12, 4, 3, 1, 13, 2, 16, 64), 256: (665, 2, 1024, 4, 9, 6, 2, 1, 14, 3, 12, 256)}
+    for pid, vals in want.items():
+        p, q = tac.params_preset(pid), ol.preset(pid)
+        got = (p.lwe_dimension, p.glwe_dimension, p.polynomial_size, p.pbs_level, p.pbs_base_log, p.ks_level, p.ks_base_log,
+               p.cbs_level, p.cbs_base_log, p.pfks_level, p.pfks_base_log, p.max_noise_level_squared)
+        assert got == vals
+        assert got == (q.n, q.k, q.N, q.pbs_l, q.pbs_b, q.ks_l, q.ks_b, q.cbs_l, q.cbs_b, q.pfks_l, q.pfks_b, q.max_noise_sq)
+        assert (p.lwe_noise_std, p.glwe_noise_std, p.pfks_noise_std) == (q.s_lwe, q.s_glwe, q.s_pfks)
+    with pytest.raises(ValueError):
+        tac.params_preset(7)
+
+
+def test_client_keys_equal_oracle_keys(ck64, oracle64):
+    for name in ("sk_glwe", "sk_lwe", "bsk", "ksk", "pfpksk"):
+        assert np.array_equal(getattr(ck64, name), getattr(oracle64, name)), name
+    assert set(np.unique(ck64.sk_glwe)) <= {0, 1}
+    assert 0.4 < ck64.sk_glwe.mean() < 0.6
+
+
+def test_client_encrypt_decrypt_equal_oracle(ck64, oracle64):
+    bits = [0, 1, 1, 0, 1, 0, 0, 1, 1]
+    a = ck64.encrypt_bits(bits, first_index=1234)
+    assert np.array_equal(a, oracle64.encrypt_bits(bits, first_index=1234))
+    assert ck64.decrypt_bits(a).tolist() == bits
+    assert np.array_equal(ck64.decrypt_phases(a), oracle64.phases(a))
+    # fresh noise: sigma_lwe·2^64 ≈ 2^49.6
+    err = (ck64.decrypt_phases(a) - (np.array(bits, dtype=np.uint64) << np.uint64(63))).astype(np.int64)
+    assert 2.0**44 < np.abs(err).astype(float).max() < 2.0**53
+    with pytest.raises(AssertionError, match="cleartext out of bounds"):
+        ck64.encrypt_bits([2])
+    assert ck64.encrypt_bits([]).shape == (0, ck64.params.big_lwe_size)
+
+
+def test_client_other_parameter_sets(tac, ol):
+    ck = tac.ClientKey(4, seed=3)
+    assert ck.decrypt_bits(ck.encrypt_bits([1, 0, 1])).tolist() == [1, 0, 1]
+    o = ol.Oracle(4, seed=3)
+    ck.gen_eval_keys()
+    assert np.array_equal(ck.ksk, o.ksk) and np.array_equal(ck.bsk, o.bsk) and np.array_equal(ck.pfpksk, o.pfpksk)
+
+
+# --- host-side noise bookkeeping: reference shortint_woppbs_1bit.rs:484-529 (KEYS_SQRD_LVL_4)
+def test_bit_xor(tac):
+    ck = tac.ClientKey(4, seed=11)
+    b1, b2, b3, b4 = (ck.encrypt(v) for v in (0, 1, 0, 1))
+    assert ck.decrypt(b1 ^ b2) == 1
+    assert ck.decrypt(b1 ^ b3) == 0
+    assert ck.decrypt(b2 ^ b4) == 0
+    t0 = ck.context.trivial(0)
+    assert ck.decrypt(b2 ^ t0) == 1
+    _ = t0 ^ t0 ^ t0                      # trivial does not accumulate noise
+    assert ck.decrypt(ck.context.trivial(1)) == 1
+
+
+def test_bit_xor_above_max_noise(tac):
+    ck = tac.ClientKey(4, seed=11)
+    bs = [ck.encrypt(v) for v in (0, 1, 0, 1, 0)]
+    with pytest.raises(tac.NoiseTooBig, match="NoiseTooBig"):
+        _ = bs[0] ^ bs[1] ^ bs[2] ^ bs[3] ^ bs[4]
+
+
+def test_bit_xor_not_independent(tac):
+    ck = tac.ClientKey(4, seed=11)
+    b1 = ck.encrypt(0)
+    with pytest.raises(AssertionError, match="noise components not independent"):
+        _ = b1 ^ b1
+
+
+def test_context_creation_fails_loudly_without_gpu(tac):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="tac_ctx_create failed"):
+        tac.FheContext(64)

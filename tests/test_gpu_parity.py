@@ -1,0 +1,299 @@
+"""GPU parity tests (run on the B200 box with -m gpu): every stage of the hot path through the C ABI against the oracle
+on identical keys and identical inputs.
+
+Bars:
+  * integer stages (keyswitch, PFKS, sample extraction, leveled adds, LUT indexing) — bit-exact;
+  * one external-product step (f64 FFT) — |Δ| < 2^35 of 2^64 per coefficient (2^-29 relative; different FFT operation order);
+  * multi-step f64 stages (PBS = 677 steps, vertical packing = 8 steps) — raw words of two correct runs diverge as soon as
+    one low digit differs, so they are compared on the decrypted phase: same message, and phase error within the noise
+    the oracle itself shows;
+  * everything end to end — decrypts to clear AES / the clear function.
+"""
+import numpy as np
+import pytest
+
+from conftest import SEED, sbox_gal_mul_fn
+
+pytestmark = pytest.mark.gpu
+
+
+def signed(x):
+    return np.asarray(x, dtype=np.uint64).astype(np.int64).astype(np.float64)
+
+
+# ---------------------------------------------------------------------------------------------- integer stages: bit-exact
+@pytest.mark.parametrize("n", [1, 17, 300])
+def test_keyswitch_bit_exact(gpu64, oracle64, n):
+    ck, ctx = gpu64
+    rng = np.random.default_rng(n)
+    cts = ck.encrypt_bits(rng.integers(0, 2, n))
+    got = ctx.stage_keyswitch(cts)
+    assert np.array_equal(got, oracle64.keyswitch(cts))
+    # and it still decrypts under the small key
+    ph = oracle64.phases_small(got)
+    assert ((ph + np.uint64(1 << 62)) >> np.uint64(63)).tolist() == ck.decrypt_bits(cts).tolist()
+
+
+def test_keyswitch_edge_inputs(gpu64, oracle64):
+    ck, ctx = gpu64
+    L = ck.params.big_lwe_size
+    cts = np.zeros((4, L), dtype=np.uint64)
+    cts[1, :] = np.uint64(2**64 - 1)
+    cts[2, :] = np.uint64(1 << 63)
+    cts[3, ::2] = np.uint64((1 << 63) + (1 << 51))          # decomposition ties
+    assert np.array_equal(ctx.stage_keyswitch(cts), oracle64.keyswitch(cts))
+
+
+@pytest.mark.parametrize("n", [1, 20, 260])
+def test_pfks_bit_exact(gpu64, oracle64, n):
+    ck, ctx = gpu64
+    rng = np.random.default_rng(100 + n)
+    x = rng.integers(0, 2**64, (n, ck.params.big_lwe_size), dtype=np.uint64)
+    x[0, :8] = [0, 2**64 - 1, 1 << 63, (1 << 63) - 1, 1 << 47, (1 << 47) - 1, (1 << 31), (1 << 63) + (1 << 31)]
+    got = ctx.stage_pfks(x)
+    assert np.array_equal(got, oracle64.pfks(x))
+
+
+def test_lwe_add_batch_bit_exact(gpu64):
+    ck, ctx = gpu64
+    rng = np.random.default_rng(3)
+    a = rng.integers(0, 2**64, (37, ck.params.big_lwe_size), dtype=np.uint64)
+    b = rng.integers(0, 2**64, (37, ck.params.big_lwe_size), dtype=np.uint64)
+    assert np.array_equal(ctx.lwe_add_batch(a, b), a + b)
+    assert ctx.lwe_add_batch(a[:0], b[:0]).shape == (0, ck.params.big_lwe_size)
+
+
+# ---------------------------------------------------------------------------------------------- f64 core: tolerance
+def _rot_diff(a, r, N):
+    idx = (np.arange(N) - r) % (2 * N)
+    rotd = np.where(idx < N, a[:, idx % N], (-a[:, idx % N].astype(np.int64)).astype(np.uint64))
+    return rotd - a
+
+
+@pytest.mark.parametrize("levels,blog", [(3, 12), (1, 13)])
+def test_cmux_rotate_step_tolerance(gpu64, oracle64, levels, blog):
+    ck, ctx = gpu64
+    p = ck.params
+    G, N = p.glwe_dimension + 1, p.polynomial_size
+    rng = np.random.default_rng(levels)
+    if levels == 3:
+        ggsw = np.ascontiguousarray(ck.bsk.reshape(p.lwe_dimension, 3, G, G, N)[5])
+    else:
+        x = oracle64.pbs(oracle64.keyswitch(ck.encrypt_bits([1])))
+        ggsw = oracle64.pfks(x)[0].reshape(1, G, G, N)                      # a circuit-bootstrapped GGSW of the bit 1
+    n_acc = 6
+    acc = rng.integers(0, 2**64, (n_acc, G, N), dtype=np.uint64)
+    rot = rng.integers(0, 2 * N, n_acc).astype(np.int32)
+    rot[0], rot[1] = 0, 2 * N - 1
+    got = ctx.stage_cmux_rotate(ggsw, levels, blog, acc, rot).reshape(n_acc, G, N)
+    for b in range(n_acc):
+        want = oracle64.external_product(ggsw, levels, blog, _rot_diff(acc[b], int(rot[b]), N).reshape(-1), acc[b].reshape(-1)).reshape(G, N)
+        d = np.abs(signed(got[b] - want))
+        assert d.max() < 2.0**35, (b, np.log2(d.max()))
+    assert np.array_equal(got[0], acc[0])                                    # rot = 0 ⇒ exact no-op
+
+
+def test_pbs_phase_and_noise(gpu64, oracle64):
+    """homomorphic_shift_boolean: output must encrypt bit·2^51 under the big key; error compared with the oracle's"""
+    ck, ctx = gpu64
+    bits = np.array([0, 1, 1, 0, 1, 0, 0, 1, 1, 1, 0, 0], dtype=np.uint8)
+    small = oracle64.keyswitch(ck.encrypt_bits(bits))
+    got = ctx.stage_pbs(small)
+    ref = oracle64.pbs(small)
+    want = bits.astype(np.uint64) << np.uint64(51)
+    e_gpu, e_ref = signed(ck.decrypt_phases(got) - want), signed(oracle64.phases(ref) - want)
+    # noise after blind rotation is far below the 2^50 half-gap; both implementations sit in the same band
+    assert np.abs(e_gpu).max() < 2.0**44 and np.abs(e_ref).max() < 2.0**44
+    assert np.abs(e_gpu).std() < 4 * np.abs(e_ref).std() + 2.0**30
+    # the two runs are the same computation up to f64 rounding: phases agree far below the noise bound
+    assert np.abs(e_gpu - e_ref).max() < 2.0**42
+
+
+def test_vertical_packing_from_oracle_ggsws(gpu64, oracle64, ol):
+    ck, ctx = gpu64
+    f = sbox_gal_mul_fn(ol)
+    lut = ctx.generate_lookup_table(8, 24, f)
+    vals = [0x00, 0x53]
+    ggsw = np.stack([oracle64.pfks(oracle64.pbs(oracle64.keyswitch(ck.encrypt_bytes([v])[0]))) for v in vals])
+    got = ctx.stage_vertical_packing(ggsw, lut)
+    for i, v in enumerate(vals):
+        ref = oracle64.vertical_packing(ggsw[i], 8, lut.table, 24)
+        assert ck.decrypt_bytes(got[i]) == f(v).to_bytes(3, "big") == oracle64.decrypt_bytes(ref)
+        want = ck.decrypt_bits(ref).astype(np.uint64) << np.uint64(63)
+        e_gpu, e_ref = signed(ck.decrypt_phases(got[i]) - want), signed(ck.decrypt_phases(ref) - want)
+        assert np.abs(e_gpu).max() < 2.0**59 and np.abs(e_gpu - e_ref).max() < 2.0**50
+
+
+# ---------------------------------------------------------------------------------------------- the operator, decrypt-checked
+def test_sbox_gal_mul_all_256_bytes(gpu64, ol):
+    """BASELINE config 2: the 8-in/24-out SBOX·{1,2,3} WoP-PBS, all byte values in one batch"""
+    ck, ctx = gpu64
+    f = sbox_gal_mul_fn(ol)
+    lut = ctx.generate_lookup_table(8, 24, f)
+    cts = ck.encrypt_bytes(bytes(range(256)))
+    out = ctx.circuit_bootstrap_batch(cts, lut)
+    dec = ck.decrypt_bytes(out.reshape(-1, ck.params.big_lwe_size))
+    assert dec == b"".join(f(v).to_bytes(3, "big") for v in range(256))
+    # measured phase-error variance must stay inside the model's bound: output noise² = 8·NOMINAL (reference :325) and
+    # max_noise_level_squared = 64 must still decode: after the worst-case 33-term sum the error stays below 2^62
+    want = ck.decrypt_bits(out.reshape(-1, ck.params.big_lwe_size)).astype(np.uint64) << np.uint64(63)
+    err = signed(ck.decrypt_phases(out) - want)
+    sigma = err.std()
+    assert sigma < 2.0**57, np.log2(sigma)
+    assert 8 * np.sqrt(33.0) * sigma < 2.0**62                     # 8σ of the MixColumns+AddRoundKey sum still decodes
+
+
+@pytest.mark.parametrize("batch", [1, 2, 40])
+def test_wopbs_batch_sizes_match_oracle(gpu64, oracle64, ol, batch):
+    """small batches take the B=1 / B=2 PBS kernels and the small GEMM tile; decrypted result equals the oracle's"""
+    ck, ctx = gpu64
+    rng = np.random.default_rng(batch)
+    lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    vals = rng.integers(0, 256, batch).tolist()
+    cts = ck.encrypt_bytes(bytes(vals))
+    out = ctx.circuit_bootstrap_batch(cts, lut)
+    assert ck.decrypt_bytes(out.reshape(-1, ck.params.big_lwe_size)) == bytes(ol.sbox(v) for v in vals)
+    if batch <= 2:
+        ref = oracle64.circuit_bootstrap(cts, lut.table, 8)
+        assert oracle64.decrypt_bytes(ref.reshape(-1, oracle64.big1)) == bytes(ol.sbox(v) for v in vals)
+
+
+def test_wopbs_empty_batch(gpu64, ol):
+    ck, ctx = gpu64
+    lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    out = ctx.circuit_bootstrap_batch(np.zeros((0, 8, ck.params.big_lwe_size), dtype=np.uint64), lut)
+    assert out.shape == (0, 8, ck.params.big_lwe_size)
+
+
+# ---------------------------------------------------------------------------------------------- reference model tests (shortint_woppbs_1bit.rs:531-617, :792-877)
+@pytest.mark.parametrize("bits,words", [(3, [0b001, 0b000, 0b100, 0b101]), (8, [0b11001001, 0b01001001, 0b00101010, 0b11011001])])
+def test_multivariate_parity_fn(gpu64, tac, bits, words):
+    ck, ctx = gpu64
+    parity_fn = lambda val: sum(tac.u16_to_bits(val)) % 2
+    tv = ctx.generate_lookup_table(bits, 1, parity_fn)
+    for word in words:
+        bit_cts = [ck.encrypt(b) for b in tac.u16_to_bits(word)]
+        d = ctx.circuit_bootstrap(bit_cts[16 - bits:], tv)[0]
+        assert ck.decrypt(d) == parity_fn(word)
+        assert d.noise_level.noise_level_squared == bits                  # NOMINAL × input_bit_count (:325)
+
+
+@pytest.mark.parametrize("bits,words", [(3, [0b101, 0b000, 0b100]), (8, [0b11001001, 0b01001001, 0b00101010, 0b11011001])])
+def test_multivariate_multivalued_square_fn(gpu64, tac, bits, words):
+    ck, ctx = gpu64
+    square_fn = lambda val: (val * val) % (1 << bits)
+    tv = ctx.generate_lookup_table(bits, bits, square_fn)
+    for byte in words:
+        bit_cts = [ck.encrypt(b) for b in tac.u16_to_bits(byte)]
+        out = ctx.circuit_bootstrap(bit_cts[16 - bits:], tv)
+        got = sum(ck.decrypt(d) << (bits - 1 - i) for i, d in enumerate(out))
+        assert got == square_fn(byte)
+
+
+def test_increment_1bit_adder_with_trivial_carry(gpu64, tac):
+    """reference :792-836 — a trivial (noiseless) ciphertext as circuit_bootstrap input"""
+    ck, ctx = gpu64
+    add_fn = lambda val: ((val >> 1) & 1) + (val & 1)
+    lut = ctx.generate_lookup_table(2, 2, add_fn)
+    value = [ck.encrypt(0) for _ in range(4)]                               # 4-bit counter, MSB first
+    for expect in (1, 2):
+        carry = ctx.trivial(1)
+        new = []
+        for bit in reversed(value):
+            carry, nb = ctx.circuit_bootstrap([carry, bit], lut)
+            new.append(nb)
+        value = list(reversed(new))
+        assert sum(ck.decrypt(b) << (3 - i) for i, b in enumerate(value)) == expect
+
+
+def test_xor_of_bootstrapped_bits_respects_bookkeeping(gpu64, tac):
+    ck, ctx = gpu64
+    ident = ctx.generate_lookup_table(1, 1, lambda b: b)
+    a, b = ck.encrypt(1), ck.encrypt(0)
+    a2 = ctx.circuit_bootstrap([a], ident)[0]
+    b2 = ctx.circuit_bootstrap([b], ident)[0]
+    c = a2 ^ b2
+    assert ck.decrypt(c) == 1 and c.noise_level.noise_level_squared == 2
+    with pytest.raises(AssertionError, match="noise components not independent"):
+        _ = c ^ a2
+
+
+# ---------------------------------------------------------------------------------------------- AES
+def test_aes_light_two_rounds(gpu64, ol):
+    """reference test_light_gal_mul (fhe_impls/shortint_woppbs_1bit.rs:185-193 → test_helper.rs:86-120): 2 rounds,
+    clear key schedule encrypted directly, one block from the ChaCha20 seed-0 stream; BASELINE config 3."""
+    ck, ctx = gpu64
+    s = ol.chacha20_stream(32)
+    key, blk = s[:16], s[16:32]
+    ctx.aes_set_key_schedule(ck.encrypt_bytes(bytes(ol.plain_key_schedule(key))))
+    enc = ctx.aes_encrypt_blocks(ck.encrypt_bytes(blk)[None], rounds=2)
+    assert ck.decrypt_bytes(enc[0]).hex() == "5c864f984df12113a07c22a99f49f0a1" == ol.plain_encrypt_block(key, blk, 2).hex()
+    enc1 = ctx.aes_encrypt_blocks(ck.encrypt_bytes(blk)[None], rounds=1)
+    assert ck.decrypt_bytes(enc1[0]).hex() == "de3011192c24fd50c3b199187f869fa4"
+
+
+def test_aes_light_matches_oracle_phase_band(gpu64, oracle64, ol):
+    """same 2-round block through the oracle on the same ciphertexts: same plaintext, comparable output noise"""
+    ck, ctx = gpu64
+    s = ol.chacha20_stream(32)
+    key, blk = s[:16], s[16:32]
+    ks_ct = ck.encrypt_bytes(bytes(ol.plain_key_schedule(key)), first_index=10_000)
+    b_ct = ck.encrypt_bytes(blk, first_index=50_000)
+    ctx.aes_set_key_schedule(ks_ct)
+    got = ctx.aes_encrypt_blocks(b_ct[None], rounds=2)[0]
+    ref = oracle64.aes_encrypt_blocks(ks_ct, b_ct[None], rounds=2)[0]
+    assert ck.decrypt_bytes(got) == ck.decrypt_bytes(ref) == ol.plain_encrypt_block(key, blk, 2)
+    want = ck.decrypt_bits(ref).astype(np.uint64) << np.uint64(63)
+    e_gpu, e_ref = signed(ck.decrypt_phases(got) - want), signed(ck.decrypt_phases(ref) - want)
+    assert e_gpu.std() < 2 * e_ref.std() and np.abs(e_gpu).max() < 2.0**60
+
+
+def test_aes_cli_stream_10_blocks(gpu64, ol):
+    """BASELINE config 4 (reference src/bin/main.rs with --number-of-outputs 10): counter blocks iv ‖ BE64(ctr)"""
+    from test_oracle_golden import CLI_IV, CLI_KEY, CLI_OUT
+    ck, ctx = gpu64
+    ctx.aes_set_key_schedule(ck.encrypt_bytes(bytes(ol.plain_key_schedule(CLI_KEY))))
+    blocks = np.stack([ck.encrypt_bytes(CLI_IV + ctr.to_bytes(8, "big")) for ctr in range(1, 11)])
+    enc = ctx.aes_encrypt_blocks(blocks)
+    assert [ck.decrypt_bytes(e).hex() for e in enc] == CLI_OUT
+
+
+def test_aes_noise_guard(tac):
+    """the fused path refuses a circuit whose squared noise would exceed the parameter set's maximum (NoiseTooBig)"""
+    ck = tac.ClientKey(4, seed=1).gen_eval_keys()
+    ctx = tac.FheContext(ck.params)
+    ctx.upload_keys(ck)
+    ctx.aes_set_key_schedule(np.zeros((44, 4, 8, ck.params.big_lwe_size), dtype=np.uint64))
+    with pytest.raises(tac.NoiseTooBig):
+        ctx.aes_encrypt_blocks(np.zeros((1, 16, 8, ck.params.big_lwe_size), dtype=np.uint64), rounds=2)
+
+
+def test_fhe_key_schedule_fips197(gpu64, ol):
+    """reference test_full_gal_mul / FIPS-197 C.1 (test_helper.rs:61-83): FHE key schedule on the device + 10 rounds"""
+    ck, ctx = gpu64
+    key = bytes.fromhex("000102030405060708090a0b0c0d0e0f")
+    blk = bytes.fromhex("00112233445566778899aabbccddeeff")
+    ks = ctx.aes_key_schedule(ck.encrypt_bytes(key))
+    assert ck.decrypt_bytes(ks.reshape(-1, ck.params.big_lwe_size)) == bytes(ol.plain_key_schedule(key))
+    enc = ctx.aes_encrypt_blocks(ck.encrypt_bytes(blk)[None])
+    assert ck.decrypt_bytes(enc[0]).hex() == "69c4e0d86a7b0430d8cdb78070b4c55a"
+
+
+# ---------------------------------------------------------------------------------------------- other parameter sets (N = 1024, k = 2)
+def test_lvl1_cmux_tree_16_to_8(tac):
+    """reference test_multivariate_multivalues_xor_8bit (:626-659): 16 inputs at N = 1024 — the real CMux tree"""
+    ck, ctx = tac.FheContext.generate_keys(1, seed=SEED)
+    b1, b2 = 0b11000110, 0b10101010
+    xor_fn = lambda v: (v >> 8) ^ (v & 0xFF)
+    tv = ctx.generate_lookup_table(16, 8, xor_fn)
+    out = ctx.circuit_bootstrap_batch(ck.encrypt_bytes([b1, b2]).reshape(1, 16, -1), tv)
+    assert ck.decrypt_bytes(out[0]) == bytes([b1 ^ b2])
+
+
+@pytest.mark.parametrize("pid", [4, 256])
+def test_other_parameter_sets_sbox(tac, ol, pid):
+    ck, ctx = tac.FheContext.generate_keys(pid, seed=SEED + pid)
+    lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    vals = [0x00, 0x53, 0xCA]
+    out = ctx.circuit_bootstrap_batch(ck.encrypt_bytes(bytes(vals)), lut)
+    assert ck.decrypt_bytes(out.reshape(-1, ck.params.big_lwe_size)) == bytes(ol.sbox(v) for v in vals)

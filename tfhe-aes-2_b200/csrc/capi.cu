@@ -1,0 +1,748 @@
+// capi.cu — device context, key upload, the batched circuit-bootstrap pipeline and the fused AES paths behind the C ABI
+// of include/tfhe_aes_cuda.h.  No CPU fallback: every entry point that computes fails with TAC_ERR_CUDA when there is
+// no usable CUDA device.
+#include "../../include/tfhe_aes_cuda.h"
+#include "kernels.cuh"
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+using namespace tac;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+struct Lut {
+    int n_in, n_out;
+    size_t len;          // words per output
+    uint64_t* dev;
+};
+
+enum Stage { ST_KS = 0, ST_PBS, ST_PFKS, ST_FFT, ST_VP, ST_COUNT };
+
+}  // namespace
+
+struct tac_ctx {
+    TacParams p;
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    // keys
+    cplx* bsk_f = nullptr;
+    uint64_t* ksk = nullptr;
+    uint64_t* pfpksk = nullptr;
+    uint64_t* ks_corr = nullptr;
+    uint64_t* pfks_corr = nullptr;
+    bool keys_allocated = false, keys_valid = false;
+    // tables
+    cplx* twist = nullptr;
+    cplx* wM = nullptr;
+    // LUTs
+    std::vector<Lut> luts;
+    int aes_lut24 = -1, aes_lut8 = -1, aes_lut1 = -1;
+    // AES key schedule
+    uint64_t* key_sched = nullptr;
+    // workspace
+    DevBuf ws_in, ws_out, ws_small, ws_ksdig, ws_pbs, ws_pfdig, ws_ggsw, ws_ggswf, ws_tree_a, ws_tree_b, ws_state, ws_muls, ws_misc;
+    size_t max_cts = 16384;
+    // profiling
+    bool profiling = false;
+    cudaEvent_t ev[ST_COUNT + 1] = {};
+    float stage_ms[ST_COUNT] = {};
+    uint64_t launches = 0;
+
+    int big() const { return p.k * p.N; }
+    int G() const { return p.k + 1; }
+    size_t bsk_cplx() const { return (size_t)p.n * p.pbs_l * G() * G() * (p.N / 2); }
+    size_t ksk_words() const { return (size_t)big() * p.ks_l * (p.n + 1); }
+    size_t pfpksk_words() const { return (size_t)G() * (big() + 1) * p.pfks_l * G() * p.N; }
+};
+
+namespace {
+
+int fail(tac_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CU(call)                                                                                              \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+#define TRY(call)              \
+    do {                       \
+        int rc__ = (call);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+int ensure(tac_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.cap >= bytes) return TAC_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr; b.cap = 0;
+    CU(cudaMalloc(&b.p, bytes));
+    b.cap = bytes;
+    return TAC_OK;
+}
+inline int grid1d(size_t total, int block, int sms) {
+    const size_t need = (total + block - 1) / block;
+    const size_t cap = (size_t)sms * 16;
+    return (int)std::max<size_t>(1, std::min(need, cap));
+}
+int post_launch(tac_ctx* ctx, const char* what) {
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return TAC_OK;
+}
+bool supported_shape(const TacParams& p) {
+    return (p.N == 512 && p.k == 4) || (p.N == 1024 && p.k == 2);
+}
+
+// ---------------------------------------------------------------------------------------------- launch wrappers
+template <int N>
+int launch_poly_fft(tac_ctx* ctx, const uint64_t* polys, size_t npoly, double scale, cplx* out) {
+    constexpr int M = N / 2;
+    const size_t smem = (size_t)(16 * M + 2 * M) * sizeof(cplx);
+    CU(cudaFuncSetAttribute(poly_fft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((npoly + 15) / 16);
+    poly_fft_kernel<N><<<grid, 256, smem, ctx->stream>>>(polys, npoly, scale, ctx->twist, ctx->wM, out);
+    return post_launch(ctx, "poly_fft_kernel");
+}
+int poly_fft(tac_ctx* ctx, const uint64_t* polys, size_t npoly, cplx* out) {
+    if (npoly == 0) return TAC_OK;
+    const double scale = 1.0 / (ctx->p.N / 2);
+    if (ctx->p.N == 512) return launch_poly_fft<512>(ctx, polys, npoly, scale, out);
+    return launch_poly_fft<1024>(ctx, polys, npoly, scale, out);
+}
+
+int gemm(tac_ctx* ctx, const uint32_t* dig, int nct, int Kd, const uint64_t* key, int W, int nkeys, const uint64_t* corr,
+         const uint64_t* last_col_add, size_t add_stride, uint64_t* out) {
+    if (nct == 0) return TAC_OK;
+    const int tiles = (W + 127) / 128;
+    if (nct >= 256) {
+        dim3 grid(tiles * nkeys, (nct + 63) / 64);
+        lwe_gemm_kernel<16><<<grid, 256, 0, ctx->stream>>>(dig, nct, Kd, key, W, nkeys, corr, last_col_add, add_stride, out);
+    } else {
+        dim3 grid(tiles * nkeys, (nct + 15) / 16);
+        lwe_gemm_kernel<4><<<grid, 256, 0, ctx->stream>>>(dig, nct, Kd, key, W, nkeys, corr, last_col_add, add_stride, out);
+    }
+    return post_launch(ctx, "lwe_gemm_kernel");
+}
+
+template <int N, int K, int L, int B, int NT>
+int launch_pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t alpha, uint64_t* out) {
+    typedef EpCfg<N, K, L, B> C;
+    const size_t smem = EpSmem<C>::bytes + (((size_t)B * (ctx->p.n + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
+    CU(cudaFuncSetAttribute(pbs_kernel<N, K, L, B, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const unsigned grid = (unsigned)((nct + B - 1) / B);
+    pbs_kernel<N, K, L, B, NT><<<grid, NT, smem, ctx->stream>>>(small, nct, ctx->p.n, ctx->bsk_f, ctx->p.pbs_b, alpha, ctx->twist, ctx->wM, out);
+    return post_launch(ctx, "pbs_kernel");
+}
+int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out) {
+    if (nct == 0) return TAC_OK;
+    const TacParams& p = ctx->p;
+    const uint64_t alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
+    const int sms = ctx->sm_count;
+    if (p.N == 512 && p.k == 4 && p.pbs_l == 3) {
+        if (nct >= 4 * sms) return launch_pbs<512, 4, 3, 4, 320>(ctx, small, nct, alpha, out);
+        if (nct >= 2 * sms) return launch_pbs<512, 4, 3, 2, 160>(ctx, small, nct, alpha, out);
+        return launch_pbs<512, 4, 3, 1, 128>(ctx, small, nct, alpha, out);
+    }
+    if (p.N == 1024 && p.k == 2 && p.pbs_l == 2) {
+        if (nct >= 2 * sms) return launch_pbs<1024, 2, 2, 2, 128>(ctx, small, nct, alpha, out);
+        return launch_pbs<1024, 2, 2, 1, 128>(ctx, small, nct, alpha, out);
+    }
+    if (p.N == 1024 && p.k == 2 && p.pbs_l == 4) {
+        if (nct >= 2 * sms) return launch_pbs<1024, 2, 4, 2, 128>(ctx, small, nct, alpha, out);
+        return launch_pbs<1024, 2, 4, 1, 128>(ctx, small, nct, alpha, out);
+    }
+    return fail(ctx, TAC_ERR_ARG, "pbs: unsupported (N, k, pbs_level)");
+}
+
+template <int N, int K, int L, int B, int NT>
+int launch_vp(tac_ctx* ctx, const cplx* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+              const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
+    typedef EpCfg<N, K, L, B> C;
+    const size_t smem = EpSmem<C>::bytes;
+    CU(cudaFuncSetAttribute(vp_kernel<N, K, L, B, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((n_out + B - 1) / B, nbox);
+    vp_kernel<N, K, L, B, NT><<<grid, NT, smem, ctx->stream>>>(ggsw_f, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, ctx->twist, ctx->wM, out);
+    return post_launch(ctx, "vp_kernel");
+}
+template <int N, int K, int L, int NT>
+int launch_tree(tac_ctx* ctx, const cplx* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
+                const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
+    typedef EpCfg<N, K, L, 1> C;
+    const size_t smem = EpSmem<C>::bytes + (size_t)C::G * N * sizeof(uint64_t);
+    CU(cudaFuncSetAttribute(cmux_tree_kernel<N, K, L, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(n_nodes_in / 2, n_out, nbox);
+    cmux_tree_kernel<N, K, L, NT><<<grid, NT, smem, ctx->stream>>>(ggsw_f, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log,
+                                                                  ctx->twist, ctx->wM, node_out);
+    return post_launch(ctx, "cmux_tree_kernel");
+}
+
+// vertical packing of `nbox` boxes from Fourier GGSWs ([nbox][n_in][1][G][G][M]) → out [nbox][n_out][big+1]
+int vertical_packing(tac_ctx* ctx, const Lut& lut, const cplx* ggsw_f, int nbox, uint64_t* out) {
+    const TacParams& p = ctx->p;
+    const int logN = ilog2(p.N);
+    const int tree_bits = lut.n_in > logN ? lut.n_in - logN : 0;
+    const uint64_t* init = nullptr;
+    if (tree_bits > 0) {
+        // CMux tree, level order: layer j uses GGSW (tree_bits-1-j)  ([U] wop_pbs.rs::cmux_tree_memory_optimized)
+        const size_t glwe = (size_t)ctx->G() * p.N;
+        int nodes = 1 << tree_bits;
+        TRY(ensure(ctx, ctx->ws_tree_a, (size_t)nbox * lut.n_out * (nodes / 2) * glwe * 8));
+        TRY(ensure(ctx, ctx->ws_tree_b, (size_t)nbox * lut.n_out * std::max(1, nodes / 4) * glwe * 8));
+        const uint64_t* cur = nullptr;
+        uint64_t* bufs[2] = {ctx->ws_tree_a.as<uint64_t>(), ctx->ws_tree_b.as<uint64_t>()};
+        int which = 0;
+        for (int j = 0; j < tree_bits; j++) {
+            uint64_t* dst = bufs[which];
+            if (p.N == 512) TRY((launch_tree<512, 4, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst)));
+            else TRY((launch_tree<1024, 2, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst)));
+            cur = dst; which ^= 1; nodes /= 2;
+        }
+        init = cur;
+    }
+    if (p.N == 512) {
+        if (lut.n_out >= 4) return launch_vp<512, 4, 1, 4, 320>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
+        return launch_vp<512, 4, 1, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
+    }
+    if (lut.n_out >= 2) return launch_vp<1024, 2, 1, 2, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
+    return launch_vp<1024, 2, 1, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
+}
+
+int stage_event(tac_ctx* ctx, int idx) {
+    if (!ctx->profiling) return TAC_OK;
+    CU(cudaEventRecord(ctx->ev[idx], ctx->stream));
+    return TAC_OK;
+}
+
+// keyswitch: in [nct][big+1] → small [nct][n+1]
+int stage_ks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* small) {
+    const TacParams& p = ctx->p;
+    const int big = ctx->big(), Kd = big * p.ks_l;
+    TRY(ensure(ctx, ctx->ws_ksdig, (size_t)nct * Kd * 4));
+    ks_digits_kernel<<<grid1d((size_t)nct * big, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big, p.ks_b, p.ks_l, ctx->ws_ksdig.as<uint32_t>());
+    TRY(post_launch(ctx, "ks_digits_kernel"));
+    return gemm(ctx, ctx->ws_ksdig.as<uint32_t>(), nct, Kd, ctx->ksk, p.n + 1, 1, ctx->ks_corr, in + big, (size_t)big + 1, small);
+}
+// PFKS with all k+1 keys: in [nct][big+1] → ggsw_std [nct][G][G·N]
+int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
+    const TacParams& p = ctx->p;
+    const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l;
+    TRY(ensure(ctx, ctx->ws_pfdig, (size_t)nct * Kd * 4));
+    pfks_digits_kernel<<<grid1d((size_t)nct * big1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big1, p.pfks_b, p.pfks_l, ctx->ws_pfdig.as<uint32_t>());
+    TRY(post_launch(ctx, "pfks_digits_kernel"));
+    return gemm(ctx, ctx->ws_pfdig.as<uint32_t>(), nct, Kd, ctx->pfpksk, ctx->G() * p.N, ctx->G(), ctx->pfks_corr, nullptr, 0, ggsw);
+}
+
+// the whole circuit bootstrap for `nbox` boxes resident on the device
+int wopbs_dev(tac_ctx* ctx, const Lut& lut, int nbox, const uint64_t* in, uint64_t* out) {
+    const TacParams& p = ctx->p;
+    if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
+    if (p.cbs_l != 1) return fail(ctx, TAC_ERR_ARG, "cbs_level != 1 is not supported");
+    const int big1 = ctx->big() + 1, G = ctx->G(), M = p.N / 2;
+    const size_t ggsw_words = (size_t)G * G * p.N;
+    const int max_boxes = (int)std::max<size_t>(1, ctx->max_cts / lut.n_in);
+    for (int b0 = 0; b0 < nbox; b0 += max_boxes) {
+        const int nb = std::min(max_boxes, nbox - b0);
+        const int nct = nb * lut.n_in;
+        const uint64_t* cin = in + (size_t)b0 * lut.n_in * big1;
+        uint64_t* cout = out + (size_t)b0 * lut.n_out * big1;
+        TRY(ensure(ctx, ctx->ws_small, (size_t)nct * (p.n + 1) * 8));
+        TRY(ensure(ctx, ctx->ws_pbs, (size_t)nct * big1 * 8));
+        TRY(ensure(ctx, ctx->ws_ggsw, (size_t)nct * ggsw_words * 8));
+        TRY(ensure(ctx, ctx->ws_ggswf, (size_t)nct * G * G * M * sizeof(cplx)));
+        TRY(stage_event(ctx, 0));
+        TRY(stage_ks(ctx, cin, nct, ctx->ws_small.as<uint64_t>()));                       // extract_dual_bit_from_bit
+        TRY(stage_event(ctx, 1));
+        TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), nct, ctx->ws_pbs.as<uint64_t>()));      // homomorphic_shift_boolean
+        TRY(stage_event(ctx, 2));
+        TRY(stage_pfks(ctx, ctx->ws_pbs.as<uint64_t>(), nct, ctx->ws_ggsw.as<uint64_t>()));
+        TRY(stage_event(ctx, 3));
+        TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), (size_t)nct * G * G, ctx->ws_ggswf.as<cplx>()));   // fill_with_forward_fourier
+        TRY(stage_event(ctx, 4));
+        TRY(vertical_packing(ctx, lut, ctx->ws_ggswf.as<cplx>(), nb, cout));
+        TRY(stage_event(ctx, 5));
+        if (ctx->profiling) {
+            CU(cudaEventSynchronize(ctx->ev[5]));
+            for (int s = 0; s < ST_COUNT; s++) {
+                float ms = 0;
+                CU(cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]));
+                ctx->stage_ms[s] = (b0 == 0 ? 0.f : ctx->stage_ms[s]) + ms;
+            }
+        }
+    }
+    return TAC_OK;
+}
+
+int get_lut(tac_ctx* ctx, int id, const Lut** out) {
+    if (id < 0 || id >= (int)ctx->luts.size()) return fail(ctx, TAC_ERR_STATE, "unknown LUT id");
+    *out = &ctx->luts[id];
+    return TAC_OK;
+}
+
+// LUT closures of the AES binding (reference fhe_impls/shortint_woppbs_1bit.rs:18-44, :94-129)
+uint8_t gf_mul(uint8_t a, uint8_t b) {           // src/aes_128.rs:42-56
+    uint8_t r = 0;
+    for (int i = 0; i < 8; i++) {
+        if (b & 1) r ^= a;
+        const bool hi = a & 0x80;
+        a = (uint8_t)(a << 1);
+        if (hi) a ^= 0x1b;
+        b >>= 1;
+    }
+    return r;
+}
+void sbox_table(uint8_t s[256]) {
+    // S-box generated from its definition (multiplicative inverse in GF(2^8) followed by the affine map); equals the
+    // table at src/aes_128.rs:18-35
+    uint8_t p = 1, q = 1;
+    do {
+        p = (uint8_t)(p ^ (p << 1) ^ ((p & 0x80) ? 0x1b : 0));
+        q ^= (uint8_t)(q << 1); q ^= (uint8_t)(q << 2); q ^= (uint8_t)(q << 4);
+        if (q & 0x80) q ^= 0x09;
+        const uint8_t x = (uint8_t)(q ^ (uint8_t)((q << 1) | (q >> 7)) ^ (uint8_t)((q << 2) | (q >> 6)) ^ (uint8_t)((q << 3) | (q >> 5)) ^ (uint8_t)((q << 4) | (q >> 4)));
+        s[p] = (uint8_t)(x ^ 0x63);
+    } while (p != 1);
+    s[0] = 0x63;
+}
+int ensure_aes_luts(tac_ctx* ctx) {
+    if (ctx->aes_lut24 >= 0) return TAC_OK;
+    uint8_t S[256]; sbox_table(S);
+    const int N = ctx->p.N;
+    std::vector<uint64_t> f(256), t;
+    for (int b = 0; b < 256; b++) f[b] = ((uint64_t)gf_mul(S[b], 1) << 16) | ((uint64_t)gf_mul(S[b], 2) << 8) | (uint64_t)gf_mul(S[b], 3);
+    t.resize(tac_lut_len(8, N) * 24); tac_generate_lut(8, 24, N, f.data(), t.data());
+    int id = tac_lut_register(ctx, 8, 24, t.data(), t.size()); if (id < 0) return id; ctx->aes_lut24 = id;
+    for (int b = 0; b < 256; b++) f[b] = S[b];
+    t.resize(tac_lut_len(8, N) * 8); tac_generate_lut(8, 8, N, f.data(), t.data());
+    id = tac_lut_register(ctx, 8, 8, t.data(), t.size()); if (id < 0) return id; ctx->aes_lut8 = id;
+    const uint64_t ident[2] = {0, 1};
+    t.resize(tac_lut_len(1, N)); tac_generate_lut(1, 1, N, ident, t.data());
+    id = tac_lut_register(ctx, 1, 1, t.data(), t.size()); if (id < 0) return id; ctx->aes_lut1 = id;
+    return TAC_OK;
+}
+
+}  // namespace
+
+namespace {
+// one CMux-with-rotation step per accumulator, through the vertical-packing kernel's step function (B = 1 CTA each)
+template <int N, int K, int L, int NT>
+__global__ void __launch_bounds__(NT, 1)
+cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__ rot, int base_log, const cplx* __restrict__ g_twist,
+                        const cplx* __restrict__ g_wM, uint64_t* __restrict__ acc_io) {
+    typedef EpCfg<N, K, L, 1> C;
+    typedef MacCfg<C, NT> MC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EpSmem<C> sm(smem_raw);
+    const int tid = threadIdx.x;
+    uint64_t* g = acc_io + (size_t)blockIdx.x * C::G * N;
+    for (int i = tid; i < C::M; i += NT) { sm.twist[i] = g_twist[i]; sm.wM[i] = g_wM[i]; }
+    for (int i = tid; i < C::G * N; i += NT) sm.acc[i] = g[i];
+    __syncthreads();
+    cplx outr[MC::SPT][1][C::G];
+#pragma unroll
+    for (int a = 0; a < MC::SPT; a++)
+#pragma unroll
+        for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
+    const DecompF64 dc = make_decomp(base_log, L);
+    const int r = rot[blockIdx.x];
+    ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int) { return r; }, dc, outr);
+    for (int i = tid; i < C::G * N; i += NT) g[i] = sm.acc[i];
+}
+template <int N, int K, int L>
+int launch_cmux_test(tac_ctx* ctx, const cplx* gf, const int* rot, int base_log, int n_acc, uint64_t* acc) {
+    typedef EpCfg<N, K, L, 1> C;
+    const size_t smem = EpSmem<C>::bytes;
+    CU(cudaFuncSetAttribute(cmux_rotate_test_kernel<N, K, L, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cmux_rotate_test_kernel<N, K, L, 128><<<n_acc, 128, smem, ctx->stream>>>(gf, rot, base_log, ctx->twist, ctx->wM, acc);
+    return post_launch(ctx, "cmux_rotate_test_kernel");
+}
+}  // namespace
+
+// =================================================================================================== C ABI
+extern "C" {
+
+const char* tac_last_error(tac_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+tac_ctx* tac_ctx_create(const tac_params* pp, int device) {
+    tac_ctx* ctx = nullptr;     // for the CU macro's fail(ctx, …) before allocation
+    auto bail = [&](const std::string& m) -> tac_ctx* { g_create_error = m; delete ctx; return nullptr; };
+    const TacParams p = *reinterpret_cast<const TacParams*>(pp);
+    if (!supported_shape(p)) return bail("unsupported (polynomial_size, glwe_dimension): kernels are instantiated for (512,4) and (1024,2)");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) return bail(std::string("no CUDA device: ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return bail("device index out of range");
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail(std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e));
+    if (prop.major != 10) return bail("this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
+    ctx = new tac_ctx();
+    ctx->p = p; ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    ctx->own_stream = true;
+    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+    if (const char* s = getenv("TAC_MAX_CTS")) { const long v = atol(s); if (v > 0) ctx->max_cts = (size_t)v; }
+    // twiddle tables in extended precision
+    const int N = p.N, M = N / 2;
+    std::vector<cplx> tw(M), w(M);
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int j = 0; j < M; j++) {
+        tw[j] = make_double2((double)cosl(pi * j / N), (double)sinl(pi * j / N));
+        w[j] = make_double2((double)cosl(-2.0L * pi * j / M), (double)sinl(-2.0L * pi * j / M));
+    }
+    if (cudaMalloc(&ctx->twist, M * sizeof(cplx)) != cudaSuccess || cudaMalloc(&ctx->wM, M * sizeof(cplx)) != cudaSuccess) return bail("cudaMalloc(tables) failed");
+    cudaMemcpy(ctx->twist, tw.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
+    cudaMemcpy(ctx->wM, w.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
+    return ctx;
+}
+
+void tac_ctx_destroy(tac_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->twist,
+                    (void*)ctx->wM, (void*)ctx->key_sched})
+        if (p) cudaFree(p);
+    for (auto& l : ctx->luts) cudaFree(l.dev);
+    for (DevBuf* b : {&ctx->ws_in, &ctx->ws_out, &ctx->ws_small, &ctx->ws_ksdig, &ctx->ws_pbs, &ctx->ws_pfdig, &ctx->ws_ggsw, &ctx->ws_ggswf,
+                      &ctx->ws_tree_a, &ctx->ws_tree_b, &ctx->ws_state, &ctx->ws_muls, &ctx->ws_misc})
+        if (b->p) cudaFree(b->p);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int tac_ctx_set_stream(tac_ctx* ctx, void* s) {
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->own_stream && ctx->stream) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaStreamDestroy(ctx->stream)); }
+    ctx->stream = reinterpret_cast<cudaStream_t>(s);
+    ctx->own_stream = false;
+    return TAC_OK;
+}
+int tac_ctx_sync(tac_ctx* ctx) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return TAC_OK; }
+int tac_ctx_sm_count(tac_ctx* ctx) { return ctx->sm_count; }
+int tac_ctx_set_profiling(tac_ctx* ctx, int on) { ctx->profiling = on != 0; return TAC_OK; }
+int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5]) { for (int s = 0; s < ST_COUNT; s++) out_ms[s] = ctx->stage_ms[s]; return TAC_OK; }
+uint64_t tac_ctx_launch_count(tac_ctx* ctx) { return ctx->launches; }
+
+int tac_ctx_alloc_keys(tac_ctx* ctx) {
+    CU(cudaSetDevice(ctx->device));
+    if (ctx->keys_allocated) return TAC_OK;
+    CU(cudaMalloc(&ctx->bsk_f, ctx->bsk_cplx() * sizeof(cplx)));
+    CU(cudaMalloc(&ctx->ksk, ctx->ksk_words() * 8));
+    CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_words() * 8));
+    CU(cudaMalloc(&ctx->ks_corr, (size_t)(ctx->p.n + 1) * 8));
+    CU(cudaMalloc(&ctx->pfks_corr, (size_t)ctx->G() * ctx->G() * ctx->p.N * 8));
+    ctx->keys_allocated = true;
+    return TAC_OK;
+}
+int tac_ctx_key_buffer(tac_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
+    if (!ctx->keys_allocated) return fail(ctx, TAC_ERR_STATE, "key buffers not allocated");
+    switch (which) {
+        case 0: *dev_ptr = ctx->bsk_f; *bytes = ctx->bsk_cplx() * sizeof(cplx); return TAC_OK;
+        case 1: *dev_ptr = ctx->ksk; *bytes = ctx->ksk_words() * 8; return TAC_OK;
+        case 2: *dev_ptr = ctx->pfpksk; *bytes = ctx->pfpksk_words() * 8; return TAC_OK;
+        default: return fail(ctx, TAC_ERR_ARG, "key buffer index");
+    }
+}
+// correction rows: corr[col] = (B/2)·Σ_k key[k][col], obtained by running the GEMM on constant digits B/2
+int tac_ctx_keys_ready(tac_ctx* ctx) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->keys_allocated) return fail(ctx, TAC_ERR_STATE, "key buffers not allocated");
+    const TacParams& p = ctx->p;
+    const int Kd_ks = ctx->big() * p.ks_l, Kd_pf = (ctx->big() + 1) * p.pfks_l;
+    const int Kmax = std::max(Kd_ks, Kd_pf);
+    TRY(ensure(ctx, ctx->ws_misc, (size_t)Kmax * 4));
+    std::vector<uint32_t> h(Kmax);
+    std::fill(h.begin(), h.end(), 1u << (p.ks_b - 1));
+    CU(cudaMemcpyAsync(ctx->ws_misc.p, h.data(), (size_t)Kd_ks * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(gemm(ctx, ctx->ws_misc.as<uint32_t>(), 1, Kd_ks, ctx->ksk, p.n + 1, 1, nullptr, nullptr, 0, ctx->ks_corr));
+    negate_kernel<<<grid1d(p.n + 1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->ks_corr, (size_t)p.n + 1);
+    TRY(post_launch(ctx, "negate_kernel"));
+    CU(cudaStreamSynchronize(ctx->stream));
+    std::fill(h.begin(), h.end(), 1u << (p.pfks_b - 1));
+    CU(cudaMemcpyAsync(ctx->ws_misc.p, h.data(), (size_t)Kd_pf * 4, cudaMemcpyHostToDevice, ctx->stream));
+    const size_t W = (size_t)ctx->G() * p.N;
+    TRY(gemm(ctx, ctx->ws_misc.as<uint32_t>(), 1, Kd_pf, ctx->pfpksk, (int)W, ctx->G(), nullptr, nullptr, 0, ctx->pfks_corr));
+    negate_kernel<<<grid1d(W * ctx->G(), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfks_corr, W * ctx->G());
+    TRY(post_launch(ctx, "negate_kernel"));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->keys_valid = true;
+    return TAC_OK;
+}
+int tac_ctx_upload_keys(tac_ctx* ctx, const uint64_t* bsk_std, const uint64_t* ksk, const uint64_t* pfpksk) {
+    TRY(tac_ctx_alloc_keys(ctx));
+    const TacParams& p = ctx->p;
+    CU(cudaMemcpyAsync(ctx->ksk, ksk, ctx->ksk_words() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->pfpksk, pfpksk, ctx->pfpksk_words() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // BSK: standard → Fourier on the device, in slices ([U] fft64/crypto/bootstrap.rs::fill_with_forward_fourier)
+    const size_t polys = (size_t)p.n * p.pbs_l * ctx->G() * ctx->G();
+    const size_t slice = 16384;
+    TRY(ensure(ctx, ctx->ws_misc, slice * p.N * 8));
+    for (size_t q = 0; q < polys; q += slice) {
+        const size_t cnt = std::min(slice, polys - q);
+        CU(cudaMemcpyAsync(ctx->ws_misc.p, bsk_std + q * p.N, cnt * p.N * 8, cudaMemcpyHostToDevice, ctx->stream));
+        TRY(poly_fft(ctx, ctx->ws_misc.as<uint64_t>(), cnt, ctx->bsk_f + q * (p.N / 2)));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return tac_ctx_keys_ready(ctx);
+}
+
+int tac_lut_register(tac_ctx* ctx, int n_in, int n_out, const uint64_t* table, size_t len) {
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, "cudaSetDevice");
+    const size_t per = tac_lut_len(n_in, ctx->p.N);
+    if (n_in <= 0 || n_in > 16 || n_out <= 0 || n_out > 64 || len != per * (size_t)n_out) return fail(ctx, TAC_ERR_ARG, "LUT shape does not match (n_in, n_out, N)");
+    Lut l{n_in, n_out, per, nullptr};
+    if (cudaMalloc(&l.dev, len * 8) != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, "cudaMalloc(LUT)");
+    if (cudaMemcpy(l.dev, table, len * 8, cudaMemcpyHostToDevice) != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, "cudaMemcpy(LUT)");
+    ctx->luts.push_back(l);
+    return (int)ctx->luts.size() - 1;
+}
+
+int tac_wopbs_batch_dev(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_dev, uint64_t* out_dev) {
+    CU(cudaSetDevice(ctx->device));
+    const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
+    if (batch < 0) return fail(ctx, TAC_ERR_ARG, "negative batch");
+    if (batch == 0) return TAC_OK;
+    return wopbs_dev(ctx, *lut, batch, in_dev, out_dev);
+}
+int tac_wopbs_batch(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
+    if (batch < 0) return fail(ctx, TAC_ERR_ARG, "negative batch");
+    if (batch == 0) return TAC_OK;
+    const size_t big1 = (size_t)ctx->big() + 1;
+    const size_t in_b = (size_t)batch * lut->n_in * big1 * 8, out_b = (size_t)batch * lut->n_out * big1 * 8;
+    TRY(ensure(ctx, ctx->ws_in, in_b));
+    TRY(ensure(ctx, ctx->ws_out, out_b));
+    CU(cudaMemcpyAsync(ctx->ws_in.p, in_host, in_b, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(wopbs_dev(ctx, *lut, batch, ctx->ws_in.as<uint64_t>(), ctx->ws_out.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_out.p, out_b, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+int tac_lwe_add_batch_dev(tac_ctx* ctx, uint64_t* a, const uint64_t* b, size_t n_cts) {
+    CU(cudaSetDevice(ctx->device));
+    const size_t total = n_cts * ((size_t)ctx->big() + 1);
+    if (total == 0) return TAC_OK;
+    lwe_add_kernel<<<grid1d(total, 256, ctx->sm_count), 256, 0, ctx->stream>>>(a, b, total);
+    return post_launch(ctx, "lwe_add_kernel");
+}
+int tac_lwe_add_batch(tac_ctx* ctx, uint64_t* a_host, const uint64_t* b_host, size_t n_cts) {
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = n_cts * ((size_t)ctx->big() + 1) * 8;
+    if (bytes == 0) return TAC_OK;
+    TRY(ensure(ctx, ctx->ws_in, bytes));
+    TRY(ensure(ctx, ctx->ws_out, bytes));
+    CU(cudaMemcpyAsync(ctx->ws_in.p, a_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->ws_out.p, b_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(tac_lwe_add_batch_dev(ctx, ctx->ws_in.as<uint64_t>(), ctx->ws_out.as<uint64_t>(), n_cts));
+    CU(cudaMemcpyAsync(a_host, ctx->ws_in.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ fused AES
+int tac_aes_set_key_schedule(tac_ctx* ctx, const uint64_t* ks_host) {
+    CU(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)44 * 32 * (ctx->big() + 1) * 8;
+    if (!ctx->key_sched) CU(cudaMalloc(&ctx->key_sched, bytes));
+    if (ks_host) {
+        CU(cudaMemcpyAsync(ctx->key_sched, ks_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    return TAC_OK;
+}
+int tac_aes_key_schedule_buffer(tac_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    TRY(tac_aes_set_key_schedule(ctx, nullptr));
+    *dev_ptr = ctx->key_sched; *bytes = (size_t)44 * 32 * (ctx->big() + 1) * 8;
+    return TAC_OK;
+}
+
+int tac_aes_encrypt_blocks_dev(tac_ctx* ctx, int n_blocks, int rounds, int in_noise_sq, const uint64_t* in_dev, uint64_t* out_dev) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->key_sched) return fail(ctx, TAC_ERR_STATE, "no key schedule on the device (tac_aes_set_key_schedule)");
+    if (n_blocks < 0 || rounds < 1 || rounds > 10) return fail(ctx, TAC_ERR_ARG, "n_blocks / rounds out of range");
+    if (n_blocks == 0) return TAC_OK;
+    // static squared-noise bookkeeping (NoiseLevelWithComponents::add_assign, shortint_woppbs_1bit.rs:63-77): round keys
+    // are fresh or bootstrapped (level 1); SBOX outputs carry 8·NOMINAL (:325)
+    const int maxn = ctx->p.max_noise_sq;
+    if (in_noise_sq + 1 > maxn || (rounds > 1 && 4 * 8 + 1 > maxn) || 8 + 1 > maxn)
+        return fail(ctx, TAC_ERR_NOISE, "NoiseTooBig: the AES circuit needs max_noise_level_squared >= 33");
+    TRY(ensure_aes_luts(ctx));
+    const size_t L = (size_t)ctx->big() + 1, blk = 16 * 8 * L;
+    const size_t total = (size_t)n_blocks * blk;
+    TRY(ensure(ctx, ctx->ws_state, total * 8));
+    TRY(ensure(ctx, ctx->ws_muls, total * 3 * 8));
+    uint64_t* state = ctx->ws_state.as<uint64_t>();
+    uint64_t* muls = ctx->ws_muls.as<uint64_t>();
+    const int g = grid1d(total, 256, ctx->sm_count);
+    aes_add_round_key_kernel<<<g, 256, 0, ctx->stream>>>(in_dev, ctx->key_sched, blk, total, state);          // :96-99
+    TRY(post_launch(ctx, "aes_add_round_key_kernel"));
+    for (int rd = 1; rd < rounds; rd++) {
+        TRY(wopbs_dev(ctx, ctx->luts[ctx->aes_lut24], n_blocks * 16, state, muls));                          // sub_bytes_with_gal_mul :27-48
+        aes_mix_columns_kernel<<<g, 256, 0, ctx->stream>>>(muls, ctx->key_sched + (size_t)rd * blk, (int)L, total, state);
+        TRY(post_launch(ctx, "aes_mix_columns_kernel"));
+    }
+    TRY(wopbs_dev(ctx, ctx->luts[ctx->aes_lut8], n_blocks * 16, state, muls));                               // sub_bytes :51-58
+    aes_final_round_kernel<<<g, 256, 0, ctx->stream>>>(muls, ctx->key_sched + (size_t)10 * blk, (int)L, total, out_dev);
+    return post_launch(ctx, "aes_final_round_kernel");
+}
+int tac_aes_encrypt_blocks(tac_ctx* ctx, int n_blocks, int rounds, int in_noise_sq, const uint64_t* in_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (n_blocks <= 0) return n_blocks == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative n_blocks");
+    const size_t bytes = (size_t)n_blocks * 128 * (ctx->big() + 1) * 8;
+    TRY(ensure(ctx, ctx->ws_in, bytes));
+    TRY(ensure(ctx, ctx->ws_out, bytes));
+    CU(cudaMemcpyAsync(ctx->ws_in.p, in_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(tac_aes_encrypt_blocks_dev(ctx, n_blocks, rounds, in_noise_sq, ctx->ws_in.as<uint64_t>(), ctx->ws_out.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_out.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+// fhe_sbox_gal_mul_pbs::key_schedule (:134-164) with boot_word (:166-180) and sub_word (:182-191) on the device
+int tac_aes_key_schedule(tac_ctx* ctx, const uint64_t* key_bits_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (8 + 1 > ctx->p.max_noise_sq) return fail(ctx, TAC_ERR_NOISE, "NoiseTooBig: key schedule needs max_noise_level_squared >= 9");
+    TRY(ensure_aes_luts(ctx));
+    TRY(tac_aes_set_key_schedule(ctx, nullptr));
+    const size_t L = (size_t)ctx->big() + 1, byte = 8 * L, word = 4 * byte;
+    uint64_t* ek = ctx->key_sched;
+    TRY(ensure(ctx, ctx->ws_state, 3 * word * 8));
+    uint64_t* rot = ctx->ws_state.as<uint64_t>();       // rotated previous word / its SBOX image
+    uint64_t* sub = rot + word;
+    uint64_t* acc = sub + word;
+    CU(cudaMemcpyAsync(ek, key_bits_host, 4 * word * 8, cudaMemcpyHostToDevice, ctx->stream));
+    // trivial(RC) constants: body += encode_bit(1) on the set bits of RC[i/4], byte 0 (:154; Byte::trivial data_model.rs:35-43)
+    static const uint8_t RC[11] = {0x00, 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36};
+    std::vector<uint64_t> rcv(byte);
+    TRY(ensure(ctx, ctx->ws_misc, byte * 8));
+    for (int i = 4; i < 44; i++) {
+        uint64_t* cur = ek + (size_t)i * word;
+        const uint64_t* prev = ek + (size_t)(i - 1) * word;
+        const uint64_t* addend = prev;
+        if (i % 4 == 0) {
+            // rotate_left(1): bytes [1,2,3,0]
+            CU(cudaMemcpyAsync(rot, prev + byte, 3 * byte * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            CU(cudaMemcpyAsync(rot + 3 * byte, prev, byte * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            TRY(wopbs_dev(ctx, ctx->luts[ctx->aes_lut8], 4, rot, sub));                                       // sub_word
+            std::fill(rcv.begin(), rcv.end(), 0ull);
+            for (int bit = 0; bit < 8; bit++)
+                if (RC[i / 4] & (0x80 >> bit)) rcv[(size_t)bit * L + (L - 1)] = tac_encode_bit(1);
+            CU(cudaMemcpyAsync(ctx->ws_misc.p, rcv.data(), byte * 8, cudaMemcpyHostToDevice, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            TRY(tac_lwe_add_batch_dev(ctx, sub, ctx->ws_misc.as<uint64_t>(), 8));
+            addend = sub;
+        }
+        CU(cudaMemcpyAsync(acc, ek + (size_t)(i - 4) * word, word * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        TRY(tac_lwe_add_batch_dev(ctx, acc, addend, 32));
+        TRY(wopbs_dev(ctx, ctx->luts[ctx->aes_lut1], 32, acc, cur));                                          // boot_word → bootstrap_assign
+    }
+    if (out_host) CU(cudaMemcpyAsync(out_host, ek, 44 * word * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ single stages
+int tac_stage_keyswitch(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
+    if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
+    const size_t ib = (size_t)n * (ctx->big() + 1) * 8, ob = (size_t)n * (ctx->p.n + 1) * 8;
+    TRY(ensure(ctx, ctx->ws_in, ib)); TRY(ensure(ctx, ctx->ws_small, ob));
+    CU(cudaMemcpyAsync(ctx->ws_in.p, in_host, ib, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(stage_ks(ctx, ctx->ws_in.as<uint64_t>(), n, ctx->ws_small.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_small.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+int tac_stage_pbs(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
+    if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
+    const size_t ib = (size_t)n * (ctx->p.n + 1) * 8, ob = (size_t)n * (ctx->big() + 1) * 8;
+    TRY(ensure(ctx, ctx->ws_small, ib)); TRY(ensure(ctx, ctx->ws_pbs, ob));
+    CU(cudaMemcpyAsync(ctx->ws_small.p, in_host, ib, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), n, ctx->ws_pbs.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_pbs.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+int tac_stage_pfks(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
+    if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
+    const size_t ib = (size_t)n * (ctx->big() + 1) * 8, ob = (size_t)n * ctx->G() * ctx->G() * ctx->p.N * 8;
+    TRY(ensure(ctx, ctx->ws_pbs, ib)); TRY(ensure(ctx, ctx->ws_ggsw, ob));
+    CU(cudaMemcpyAsync(ctx->ws_pbs.p, in_host, ib, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(stage_pfks(ctx, ctx->ws_pbs.as<uint64_t>(), n, ctx->ws_ggsw.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_ggsw.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64_t* ggsw_std_host, uint64_t* out_host) {
+    CU(cudaSetDevice(ctx->device));
+    const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
+    if (ctx->p.cbs_l != 1) return fail(ctx, TAC_ERR_ARG, "cbs_level != 1 is not supported");
+    if (batch <= 0) return batch == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative batch");
+    const int G = ctx->G(), M = ctx->p.N / 2;
+    const size_t nct = (size_t)batch * lut->n_in;
+    const size_t ib = nct * G * G * ctx->p.N * 8, ob = (size_t)batch * lut->n_out * (ctx->big() + 1) * 8;
+    TRY(ensure(ctx, ctx->ws_ggsw, ib)); TRY(ensure(ctx, ctx->ws_ggswf, nct * G * G * M * sizeof(cplx))); TRY(ensure(ctx, ctx->ws_out, ob));
+    CU(cudaMemcpyAsync(ctx->ws_ggsw.p, ggsw_std_host, ib, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), nct * G * G, ctx->ws_ggswf.as<cplx>()));
+    TRY(vertical_packing(ctx, *lut, ctx->ws_ggswf.as<cplx>(), batch, ctx->ws_out.as<uint64_t>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+int tac_stage_cmux_rotate(tac_ctx* ctx, int levels, int base_log, const uint64_t* ggsw_std_host, int n_acc, const int32_t* rot, uint64_t* acc_host) {
+    CU(cudaSetDevice(ctx->device));
+    if (n_acc <= 0) return n_acc == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
+    const TacParams& p = ctx->p;
+    const int G = ctx->G(), M = p.N / 2;
+    const size_t polys = (size_t)levels * G * G;
+    const size_t ab = (size_t)n_acc * G * p.N * 8;
+    TRY(ensure(ctx, ctx->ws_ggsw, polys * p.N * 8)); TRY(ensure(ctx, ctx->ws_ggswf, polys * M * sizeof(cplx)));
+    TRY(ensure(ctx, ctx->ws_out, ab)); TRY(ensure(ctx, ctx->ws_misc, (size_t)n_acc * 4));
+    CU(cudaMemcpyAsync(ctx->ws_ggsw.p, ggsw_std_host, polys * p.N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->ws_out.p, acc_host, ab, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->ws_misc.p, rot, (size_t)n_acc * 4, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), polys, ctx->ws_ggswf.as<cplx>()));
+    int rc = TAC_ERR_ARG;
+    const cplx* gf = ctx->ws_ggswf.as<cplx>(); const int* r = ctx->ws_misc.as<int>(); uint64_t* a = ctx->ws_out.as<uint64_t>();
+    if (p.N == 512 && p.k == 4) {
+        if (levels == 1) rc = launch_cmux_test<512, 4, 1>(ctx, gf, r, base_log, n_acc, a);
+        else if (levels == 3) rc = launch_cmux_test<512, 4, 3>(ctx, gf, r, base_log, n_acc, a);
+    } else if (p.N == 1024 && p.k == 2) {
+        if (levels == 1) rc = launch_cmux_test<1024, 2, 1>(ctx, gf, r, base_log, n_acc, a);
+        else if (levels == 2) rc = launch_cmux_test<1024, 2, 2>(ctx, gf, r, base_log, n_acc, a);
+        else if (levels == 4) rc = launch_cmux_test<1024, 2, 4>(ctx, gf, r, base_log, n_acc, a);
+    }
+    if (rc == TAC_ERR_ARG) return fail(ctx, TAC_ERR_ARG, "cmux_rotate: unsupported level count for this parameter set");
+    TRY(rc);
+    CU(cudaMemcpyAsync(acc_host, ctx->ws_out.p, ab, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
+}  // extern "C"

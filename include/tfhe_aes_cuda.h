@@ -135,11 +135,14 @@ int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64
  * acc: [n_acc][(k+1)N] in/out, rot[n_acc] in [0, 2N).  Exercises the FFT / external-product core alone. */
 int tac_stage_cmux_rotate(tac_ctx* ctx, int levels, int base_log, const uint64_t* ggsw_std_host, int n_acc, const int32_t* rot,
                           uint64_t* acc_host);
-/* per-stage device time (ms, CUDA events) of the last tac_wopbs_batch* call when profiling is on:
- * [0] keyswitch [1] PBS [2] PFKS [3] GGSW FFT [4] vertical packing.  Kernel launch counter since creation. */
+/* Per-stage device time.  With profiling on, every pipeline pass records CUDA events on the context's stream (no host
+ * synchronisation); tac_ctx_stage_times synchronises, returns the summed milliseconds since the previous call —
+ * [0] keyswitch [1] PBS [2] PFKS [3] GGSW FFT [4] vertical packing — and the number of passes, then resets. */
 int tac_ctx_set_profiling(tac_ctx* ctx, int on);
-int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5]);
-uint64_t tac_ctx_launch_count(tac_ctx* ctx);
+int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5], int* n_passes);
+uint64_t tac_ctx_launch_count(tac_ctx* ctx);                 /* kernels launched since creation */
+/* FP64 FMA-pipe throughput of this GPU in TFLOP/s (DFMA microbenchmark): the roofline denominator of the PBS kernel */
+int tac_bench_fp64_peak(tac_ctx* ctx, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -8,27 +8,16 @@
 
 using namespace tac;
 
-template <int N>
-static void build_tables(std::vector<cplx>& twist, std::vector<cplx>& wM) {
-    const int M = N / 2;
-    const long double pi = 3.141592653589793238462643383279502884L;
-    twist.resize(M); wM.resize(M);
-    for (int j = 0; j < M; j++) {
-        twist[j] = mk((double)cosl(pi * j / N), (double)sinl(pi * j / N));
-        wM[j] = mk((double)cosl(-2.0L * pi * j / M), (double)sinl(-2.0L * pi * j / M));
-    }
-}
-
 template <int N, int K, int L, int B, int NT>
 static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
     typedef EpCfg<N, K, L, B> C;
     typedef MacCfg<C, NT> MC;
-    std::vector<cplx> twist, wM; build_tables<N>(twist, wM);
+    std::vector<cplx> wT(C::M); build_wT(N, wT.data());
     // Fourier GGSW with the kernels' own key transform
     const int polys = L * C::G * C::G;
     std::vector<cplx> gf((size_t)polys * C::M), buf(C::M);
     for (int q = 0; q < polys; q++) {
-        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, twist.data(), wM.data(), buf.data());
+        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, wT.data(), buf.data());
         for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, buf.data());
         for (int s = 0; s < C::M; s++) gf[(size_t)q * C::M + s] = buf[s];
     }
@@ -36,29 +25,37 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     std::vector<Regs> regs(NT);
     for (auto& r : regs) for (int a = 0; a < MC::SPT; a++) for (int b = 0; b < C::B; b++) for (int c = 0; c < C::G; c++) r.v[a][b][c] = mk(0, 0);
     std::vector<cplx> S(C::s_cplx);
-    const DecompF64 dc = make_decomp(base_log, L);
+    std::vector<uint32_t> dig(C::dig_words);
+    auto coef = [&](int job, int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); };
+    for (int tid = 0; tid < NT; tid++) ph_decomp<C>(tid, NT, coef, base_log, dig.data());
     for (int lev = L; lev >= 1; lev--) {
-        for (int tid = 0; tid < NT; tid++) ph_fwd1<C>(tid, NT, lev, acc, [&](int b) { return rot[b]; }, dc, twist.data(), wM.data(), S.data());
+        for (int tid = 0; tid < NT; tid++) ph_fwd1<C>(tid, NT, lev, dig.data(), wT.data(), S.data());
         for (int tid = 0; tid < NT; tid++) ph_fwd2<C>(tid, NT, S.data());
         for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, gf.data(), S.data(), regs[tid].v);
     }
     for (int tid = 0; tid < NT; tid++) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, S.data(), regs[tid].v);
-    for (int tid = 0; tid < NT; tid++) ph_inv1<C>(tid, NT, wM.data(), S.data());
-    for (int tid = 0; tid < NT; tid++) ph_inv2<C>(tid, NT, twist.data(), S.data(), acc);
+    for (int tid = 0; tid < NT; tid++) ph_inv1<C>(tid, NT, wT.data(), S.data());
+    for (int tid = 0; tid < NT; tid++) ph_inv2<C>(tid, NT, S.data(), acc);
 }
 
 // forward transform of a real polynomial given as doubles; returns slot-ordered spectrum + the frequency held by each slot
 template <int N>
 static void emul_fft(const double* in, double* out_re, double* out_im, int* slot_freq) {
     const int M = N / 2, P = M / 16;
-    std::vector<cplx> twist, wM, S(M); build_tables<N>(twist, wM);
-    for (int t = 0; t < 16; t++) fft_fwd_pass1<N>(t, [&](int j) { return in[j]; }, twist.data(), wM.data(), S.data());
+    std::vector<cplx> wT(M), S(M); build_wT(N, wT.data());
+    for (int t = 0; t < 16; t++) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { a = in[jj]; b = in[jj + M]; }, wT.data(), S.data());
     for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, S.data());
     for (int s = 0; s < M; s++) { out_re[s] = S[s].x; out_im[s] = S[s].y; }
     for (int q = 0; q < P; q++) for (int i = 0; i < 16; i++) slot_freq[slot_of(q, i)] = q + P * bitrev<16>(i);
     // inverse back into `in`-shaped output appended after the spectrum (roundtrip check): out_re[M..M+N)
-    for (int t = 0; t < 16; t++) fft_inv_passA<N>(t, wM.data(), S.data());
-    for (int t = 0; t < 16; t++) fft_inv_passB<N>(t, twist.data(), S.data(), 1.0 / M, [&](int j, double v) { out_re[M + j] = v; });
+    for (int t = 0; t < 16; t++) fft_inv_passA<N>(t, wT.data(), S.data());
+    for (int t = 0; t < 16; t++) fft_inv_passB<N>(t, S.data(), [&](int jj, double re, double im) { out_re[M + jj] = re / M; out_re[M + jj + M] = im / M; });
+}
+
+template <int L> static void digits_t(uint64_t x, int b, double* out) {
+    uint32_t w[L];
+    decompose_pair<L>(x, ~x, b, w);
+    for (int s = 0; s < L; s++) { double a, c; unpack_digits(w[s], a, c); out[s] = a; }
 }
 
 extern "C" {
@@ -76,7 +73,6 @@ int emul_fft_fwd_inv(int N, const double* in, double* out_re, double* out_im, in
 }
 uint64_t emul_f64_to_torus(double x) { return f64_to_torus(x); }
 void emul_digits(uint64_t x, int b, int l, double* out) {
-    const DecompF64 dc = make_decomp(b, l);
-    for (int lev = 1; lev <= l; lev++) out[lev - 1] = (l == 1) ? digit_f64<1>(x, dc, lev) : (l == 2) ? digit_f64<2>(x, dc, lev) : (l == 3) ? digit_f64<3>(x, dc, lev) : digit_f64<4>(x, dc, lev);
+    if (l == 1) digits_t<1>(x, b, out); else if (l == 2) digits_t<2>(x, b, out); else if (l == 3) digits_t<3>(x, b, out); else digits_t<4>(x, b, out);
 }
 }

@@ -94,7 +94,8 @@ _SIGNATURES = {
     "tac_stage_vertical_packing": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, _u64p]),
     "tac_stage_cmux_rotate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, C.c_int, _i32p, _u64p]),
     "tac_ctx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
-    "tac_ctx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "tac_ctx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "tac_bench_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
     "tac_ctx_launch_count": (C.c_uint64, [C.c_void_p]),
 }
 
@@ -410,9 +411,17 @@ class FheContext(NoiseContext):
         self._check(self.L.tac_ctx_set_profiling(self.h, int(on)))
 
     def stage_times(self):
-        arr = (C.c_float * 5)()
-        self.L.tac_ctx_stage_times(self.h, arr)
-        return dict(zip(("keyswitch", "pbs", "pfks", "ggsw_fft", "vertical_packing"), [float(x) for x in arr]))
+        """summed per-stage device ms since the last call, plus the number of pipeline passes (= PBS kernel launches)"""
+        arr, n = (C.c_float * 5)(), C.c_int()
+        self._check(self.L.tac_ctx_stage_times(self.h, arr, C.byref(n)))
+        d = dict(zip(("keyswitch", "pbs", "pfks", "ggsw_fft", "vertical_packing"), [float(x) for x in arr]))
+        d["passes"] = n.value
+        return d
+
+    def fp64_peak_tflops(self):
+        v = C.c_double()
+        self._check(self.L.tac_bench_fp64_peak(self.h, C.byref(v)))
+        return v.value
 
     def launch_count(self):
         return int(self.L.tac_ctx_launch_count(self.h))

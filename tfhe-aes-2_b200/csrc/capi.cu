@@ -2,7 +2,9 @@
 // of include/tfhe_aes_cuda.h.  No CPU fallback: every entry point that computes fails with TAC_ERR_CUDA when there is
 // no usable CUDA device.
 #include "../../include/tfhe_aes_cuda.h"
-#include "kernels.cuh"
+#include "kernels_common.cuh"
+#include "ep_step.cuh"
+#include "shape_launch.h"
 
 #include <cmath>
 #include <cstdio>
@@ -47,8 +49,8 @@ struct tac_ctx {
     uint64_t* pfks_corr = nullptr;
     bool keys_allocated = false, keys_valid = false;
     // tables
-    cplx* twist = nullptr;
-    cplx* wM = nullptr;
+    cplx* wT = nullptr;            // combined twist/twiddle table (ep_core.cuh)
+    const ShapeOps* ops = nullptr; // kernels of this (N, k)
     // LUTs
     std::vector<Lut> luts;
     int aes_lut24 = -1, aes_lut8 = -1, aes_lut1 = -1;
@@ -57,10 +59,11 @@ struct tac_ctx {
     // workspace
     DevBuf ws_in, ws_out, ws_small, ws_ksdig, ws_pbs, ws_pfdig, ws_ggsw, ws_ggswf, ws_tree_a, ws_tree_b, ws_state, ws_muls, ws_misc;
     size_t max_cts = 16384;
-    // profiling
+    // profiling: one event tuple per pipeline pass, recorded without synchronising; read back by tac_ctx_stage_times
     bool profiling = false;
-    cudaEvent_t ev[ST_COUNT + 1] = {};
-    float stage_ms[ST_COUNT] = {};
+    struct ProfRec { cudaEvent_t ev[ST_COUNT + 1]; };
+    std::vector<ProfRec> prof_pool;
+    size_t prof_used = 0;
     uint64_t launches = 0;
 
     int big() const { return p.k * p.N; }
@@ -111,20 +114,16 @@ bool supported_shape(const TacParams& p) {
 }
 
 // ---------------------------------------------------------------------------------------------- launch wrappers
-template <int N>
-int launch_poly_fft(tac_ctx* ctx, const uint64_t* polys, size_t npoly, double scale, cplx* out) {
-    constexpr int M = N / 2;
-    const size_t smem = (size_t)(16 * M + 2 * M) * sizeof(cplx);
-    CU(cudaFuncSetAttribute(poly_fft_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((npoly + 15) / 16);
-    poly_fft_kernel<N><<<grid, 256, smem, ctx->stream>>>(polys, npoly, scale, ctx->twist, ctx->wM, out);
-    return post_launch(ctx, "poly_fft_kernel");
+KLaunch klaunch(tac_ctx* ctx) { return KLaunch{ctx->stream, ctx->wT, ctx->sm_count}; }
+int check_launch(tac_ctx* ctx, cudaError_t e, const char* what) {
+    ctx->launches++;
+    if (e == cudaErrorInvalidValue) return fail(ctx, TAC_ERR_ARG, std::string(what) + ": unsupported level count / shape for this parameter set");
+    if (e != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return TAC_OK;
 }
 int poly_fft(tac_ctx* ctx, const uint64_t* polys, size_t npoly, cplx* out) {
     if (npoly == 0) return TAC_OK;
-    const double scale = 1.0 / (ctx->p.N / 2);
-    if (ctx->p.N == 512) return launch_poly_fft<512>(ctx, polys, npoly, scale, out);
-    return launch_poly_fft<1024>(ctx, polys, npoly, scale, out);
+    return check_launch(ctx, ctx->ops->poly_fft(klaunch(ctx), polys, npoly, 1.0 / (ctx->p.N / 2), out), "poly_fft_kernel");
 }
 
 int gemm(tac_ctx* ctx, const uint32_t* dig, int nct, int Kd, const uint64_t* key, int W, int nkeys, const uint64_t* corr,
@@ -141,56 +140,11 @@ int gemm(tac_ctx* ctx, const uint32_t* dig, int nct, int Kd, const uint64_t* key
     return post_launch(ctx, "lwe_gemm_kernel");
 }
 
-template <int N, int K, int L, int B, int NT>
-int launch_pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t alpha, uint64_t* out) {
-    typedef EpCfg<N, K, L, B> C;
-    const size_t smem = EpSmem<C>::bytes + (((size_t)B * (ctx->p.n + 1) * sizeof(uint16_t) + 15) & ~(size_t)15);
-    CU(cudaFuncSetAttribute(pbs_kernel<N, K, L, B, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const unsigned grid = (unsigned)((nct + B - 1) / B);
-    pbs_kernel<N, K, L, B, NT><<<grid, NT, smem, ctx->stream>>>(small, nct, ctx->p.n, ctx->bsk_f, ctx->p.pbs_b, alpha, ctx->twist, ctx->wM, out);
-    return post_launch(ctx, "pbs_kernel");
-}
 int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out) {
     if (nct == 0) return TAC_OK;
     const TacParams& p = ctx->p;
     const uint64_t alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
-    const int sms = ctx->sm_count;
-    if (p.N == 512 && p.k == 4 && p.pbs_l == 3) {
-        if (nct >= 4 * sms) return launch_pbs<512, 4, 3, 4, 320>(ctx, small, nct, alpha, out);
-        if (nct >= 2 * sms) return launch_pbs<512, 4, 3, 2, 160>(ctx, small, nct, alpha, out);
-        return launch_pbs<512, 4, 3, 1, 128>(ctx, small, nct, alpha, out);
-    }
-    if (p.N == 1024 && p.k == 2 && p.pbs_l == 2) {
-        if (nct >= 2 * sms) return launch_pbs<1024, 2, 2, 2, 128>(ctx, small, nct, alpha, out);
-        return launch_pbs<1024, 2, 2, 1, 128>(ctx, small, nct, alpha, out);
-    }
-    if (p.N == 1024 && p.k == 2 && p.pbs_l == 4) {
-        if (nct >= 2 * sms) return launch_pbs<1024, 2, 4, 2, 128>(ctx, small, nct, alpha, out);
-        return launch_pbs<1024, 2, 4, 1, 128>(ctx, small, nct, alpha, out);
-    }
-    return fail(ctx, TAC_ERR_ARG, "pbs: unsupported (N, k, pbs_level)");
-}
-
-template <int N, int K, int L, int B, int NT>
-int launch_vp(tac_ctx* ctx, const cplx* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
-              const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
-    typedef EpCfg<N, K, L, B> C;
-    const size_t smem = EpSmem<C>::bytes;
-    CU(cudaFuncSetAttribute(vp_kernel<N, K, L, B, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((n_out + B - 1) / B, nbox);
-    vp_kernel<N, K, L, B, NT><<<grid, NT, smem, ctx->stream>>>(ggsw_f, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, ctx->twist, ctx->wM, out);
-    return post_launch(ctx, "vp_kernel");
-}
-template <int N, int K, int L, int NT>
-int launch_tree(tac_ctx* ctx, const cplx* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
-                const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
-    typedef EpCfg<N, K, L, 1> C;
-    const size_t smem = EpSmem<C>::bytes + (size_t)C::G * N * sizeof(uint64_t);
-    CU(cudaFuncSetAttribute(cmux_tree_kernel<N, K, L, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid(n_nodes_in / 2, n_out, nbox);
-    cmux_tree_kernel<N, K, L, NT><<<grid, NT, smem, ctx->stream>>>(ggsw_f, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log,
-                                                                  ctx->twist, ctx->wM, node_out);
-    return post_launch(ctx, "cmux_tree_kernel");
+    return check_launch(ctx, ctx->ops->pbs(klaunch(ctx), p.pbs_l, small, nct, p.n, ctx->bsk_f, p.pbs_b, alpha, out), "pbs_kernel");
 }
 
 // vertical packing of `nbox` boxes from Fourier GGSWs ([nbox][n_in][1][G][G][M]) → out [nbox][n_out][big+1]
@@ -210,23 +164,26 @@ int vertical_packing(tac_ctx* ctx, const Lut& lut, const cplx* ggsw_f, int nbox,
         int which = 0;
         for (int j = 0; j < tree_bits; j++) {
             uint64_t* dst = bufs[which];
-            if (p.N == 512) TRY((launch_tree<512, 4, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst)));
-            else TRY((launch_tree<1024, 2, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst)));
+            TRY(check_launch(ctx, ctx->ops->tree(klaunch(ctx), ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst),
+                             "cmux_tree_kernel"));
             cur = dst; which ^= 1; nodes /= 2;
         }
         init = cur;
     }
-    if (p.N == 512) {
-        if (lut.n_out >= 4) return launch_vp<512, 4, 1, 4, 320>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
-        return launch_vp<512, 4, 1, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
-    }
-    if (lut.n_out >= 2) return launch_vp<1024, 2, 1, 2, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
-    return launch_vp<1024, 2, 1, 1, 128>(ctx, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out);
+    return check_launch(ctx, ctx->ops->vp(klaunch(ctx), ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out), "vp_kernel");
 }
 
 int stage_event(tac_ctx* ctx, int idx) {
     if (!ctx->profiling) return TAC_OK;
-    CU(cudaEventRecord(ctx->ev[idx], ctx->stream));
+    if (idx == 0) {
+        if (ctx->prof_used == ctx->prof_pool.size()) {
+            tac_ctx::ProfRec r;
+            for (auto& e : r.ev) CU(cudaEventCreate(&e));
+            ctx->prof_pool.push_back(r);
+        }
+        ctx->prof_used++;
+    }
+    CU(cudaEventRecord(ctx->prof_pool[ctx->prof_used - 1].ev[idx], ctx->stream));
     return TAC_OK;
 }
 
@@ -277,14 +234,6 @@ int wopbs_dev(tac_ctx* ctx, const Lut& lut, int nbox, const uint64_t* in, uint64
         TRY(stage_event(ctx, 4));
         TRY(vertical_packing(ctx, lut, ctx->ws_ggswf.as<cplx>(), nb, cout));
         TRY(stage_event(ctx, 5));
-        if (ctx->profiling) {
-            CU(cudaEventSynchronize(ctx->ev[5]));
-            for (int s = 0; s < ST_COUNT; s++) {
-                float ms = 0;
-                CU(cudaEventElapsedTime(&ms, ctx->ev[s], ctx->ev[s + 1]));
-                ctx->stage_ms[s] = (b0 == 0 ? 0.f : ctx->stage_ms[s]) + ms;
-            }
-        }
     }
     return TAC_OK;
 }
@@ -339,41 +288,6 @@ int ensure_aes_luts(tac_ctx* ctx) {
 
 }  // namespace
 
-namespace {
-// one CMux-with-rotation step per accumulator, through the vertical-packing kernel's step function (B = 1 CTA each)
-template <int N, int K, int L, int NT>
-__global__ void __launch_bounds__(NT, 1)
-cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__ rot, int base_log, const cplx* __restrict__ g_twist,
-                        const cplx* __restrict__ g_wM, uint64_t* __restrict__ acc_io) {
-    typedef EpCfg<N, K, L, 1> C;
-    typedef MacCfg<C, NT> MC;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    EpSmem<C> sm(smem_raw);
-    const int tid = threadIdx.x;
-    uint64_t* g = acc_io + (size_t)blockIdx.x * C::G * N;
-    for (int i = tid; i < C::M; i += NT) { sm.twist[i] = g_twist[i]; sm.wM[i] = g_wM[i]; }
-    for (int i = tid; i < C::G * N; i += NT) sm.acc[i] = g[i];
-    __syncthreads();
-    cplx outr[MC::SPT][1][C::G];
-#pragma unroll
-    for (int a = 0; a < MC::SPT; a++)
-#pragma unroll
-        for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
-    const DecompF64 dc = make_decomp(base_log, L);
-    const int r = rot[blockIdx.x];
-    ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int) { return r; }, dc, outr);
-    for (int i = tid; i < C::G * N; i += NT) g[i] = sm.acc[i];
-}
-template <int N, int K, int L>
-int launch_cmux_test(tac_ctx* ctx, const cplx* gf, const int* rot, int base_log, int n_acc, uint64_t* acc) {
-    typedef EpCfg<N, K, L, 1> C;
-    const size_t smem = EpSmem<C>::bytes;
-    CU(cudaFuncSetAttribute(cmux_rotate_test_kernel<N, K, L, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cmux_rotate_test_kernel<N, K, L, 128><<<n_acc, 128, smem, ctx->stream>>>(gf, rot, base_log, ctx->twist, ctx->wM, acc);
-    return post_launch(ctx, "cmux_rotate_test_kernel");
-}
-}  // namespace
-
 // =================================================================================================== C ABI
 extern "C" {
 
@@ -394,21 +308,16 @@ tac_ctx* tac_ctx_create(const tac_params* pp, int device) {
     if (prop.major != 10) return bail("this library is built for sm_100a (B200) only; found sm_" + std::to_string(prop.major) + std::to_string(prop.minor));
     ctx = new tac_ctx();
     ctx->p = p; ctx->device = device; ctx->sm_count = prop.multiProcessorCount;
+    ctx->ops = (p.N == 512) ? shape_ops_n512_k4() : shape_ops_n1024_k2();
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     ctx->own_stream = true;
-    for (auto& ev : ctx->ev) cudaEventCreate(&ev);
     if (const char* s = getenv("TAC_MAX_CTS")) { const long v = atol(s); if (v > 0) ctx->max_cts = (size_t)v; }
-    // twiddle tables in extended precision
-    const int N = p.N, M = N / 2;
-    std::vector<cplx> tw(M), w(M);
-    const long double pi = 3.141592653589793238462643383279502884L;
-    for (int j = 0; j < M; j++) {
-        tw[j] = make_double2((double)cosl(pi * j / N), (double)sinl(pi * j / N));
-        w[j] = make_double2((double)cosl(-2.0L * pi * j / M), (double)sinl(-2.0L * pi * j / M));
-    }
-    if (cudaMalloc(&ctx->twist, M * sizeof(cplx)) != cudaSuccess || cudaMalloc(&ctx->wM, M * sizeof(cplx)) != cudaSuccess) return bail("cudaMalloc(tables) failed");
-    cudaMemcpy(ctx->twist, tw.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
-    cudaMemcpy(ctx->wM, w.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
+    // combined twist/twiddle table in extended precision
+    const int M = p.N / 2;
+    std::vector<cplx> w(M);
+    build_wT(p.N, w.data());
+    if (cudaMalloc(&ctx->wT, M * sizeof(cplx)) != cudaSuccess) return bail("cudaMalloc(tables) failed");
+    cudaMemcpy(ctx->wT, w.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
     return ctx;
 }
 
@@ -416,14 +325,14 @@ void tac_ctx_destroy(tac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->twist,
-                    (void*)ctx->wM, (void*)ctx->key_sched})
+    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->wT,
+                    (void*)ctx->key_sched})
         if (p) cudaFree(p);
     for (auto& l : ctx->luts) cudaFree(l.dev);
     for (DevBuf* b : {&ctx->ws_in, &ctx->ws_out, &ctx->ws_small, &ctx->ws_ksdig, &ctx->ws_pbs, &ctx->ws_pfdig, &ctx->ws_ggsw, &ctx->ws_ggswf,
                       &ctx->ws_tree_a, &ctx->ws_tree_b, &ctx->ws_state, &ctx->ws_muls, &ctx->ws_misc})
         if (b->p) cudaFree(b->p);
-    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& r : ctx->prof_pool) for (auto& ev : r.ev) cudaEventDestroy(ev);
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -438,7 +347,43 @@ int tac_ctx_set_stream(tac_ctx* ctx, void* s) {
 int tac_ctx_sync(tac_ctx* ctx) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return TAC_OK; }
 int tac_ctx_sm_count(tac_ctx* ctx) { return ctx->sm_count; }
 int tac_ctx_set_profiling(tac_ctx* ctx, int on) { ctx->profiling = on != 0; return TAC_OK; }
-int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5]) { for (int s = 0; s < ST_COUNT; s++) out_ms[s] = ctx->stage_ms[s]; return TAC_OK; }
+int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5], int* n_passes) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int s = 0; s < ST_COUNT; s++) out_ms[s] = 0.f;
+    for (size_t r = 0; r < ctx->prof_used; r++)
+        for (int s = 0; s < ST_COUNT; s++) {
+            float ms = 0;
+            CU(cudaEventElapsedTime(&ms, ctx->prof_pool[r].ev[s], ctx->prof_pool[r].ev[s + 1]));
+            out_ms[s] += ms;
+        }
+    if (n_passes) *n_passes = (int)ctx->prof_used;
+    ctx->prof_used = 0;
+    return TAC_OK;
+}
+// FP64 FMA pipe peak of this GPU (the roofline denominator of the PBS kernel; not in MEASURED_PEAKS.json)
+int tac_bench_fp64_peak(tac_ctx* ctx, double* tflops) {
+    CU(cudaSetDevice(ctx->device));
+    TRY(ensure(ctx, ctx->ws_misc, 1 << 20));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    const int iters = 4096, blocks = ctx->sm_count * 8, threads = 256;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; rep++) {
+        CU(cudaEventRecord(e0, ctx->stream));
+        dfma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(ctx->ws_misc.as<double>(), iters, 1.0000001);
+        CU(cudaEventRecord(e1, ctx->stream));
+        CU(cudaEventSynchronize(e1));
+        TRY(post_launch(ctx, "dfma_peak_kernel"));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double flops = 2.0 * 16.0 * (double)iters * blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *tflops = best;
+    return TAC_OK;
+}
 uint64_t tac_ctx_launch_count(tac_ctx* ctx) { return ctx->launches; }
 
 int tac_ctx_alloc_keys(tac_ctx* ctx) {
@@ -728,18 +673,8 @@ int tac_stage_cmux_rotate(tac_ctx* ctx, int levels, int base_log, const uint64_t
     CU(cudaMemcpyAsync(ctx->ws_out.p, acc_host, ab, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(ctx->ws_misc.p, rot, (size_t)n_acc * 4, cudaMemcpyHostToDevice, ctx->stream));
     TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), polys, ctx->ws_ggswf.as<cplx>()));
-    int rc = TAC_ERR_ARG;
-    const cplx* gf = ctx->ws_ggswf.as<cplx>(); const int* r = ctx->ws_misc.as<int>(); uint64_t* a = ctx->ws_out.as<uint64_t>();
-    if (p.N == 512 && p.k == 4) {
-        if (levels == 1) rc = launch_cmux_test<512, 4, 1>(ctx, gf, r, base_log, n_acc, a);
-        else if (levels == 3) rc = launch_cmux_test<512, 4, 3>(ctx, gf, r, base_log, n_acc, a);
-    } else if (p.N == 1024 && p.k == 2) {
-        if (levels == 1) rc = launch_cmux_test<1024, 2, 1>(ctx, gf, r, base_log, n_acc, a);
-        else if (levels == 2) rc = launch_cmux_test<1024, 2, 2>(ctx, gf, r, base_log, n_acc, a);
-        else if (levels == 4) rc = launch_cmux_test<1024, 2, 4>(ctx, gf, r, base_log, n_acc, a);
-    }
-    if (rc == TAC_ERR_ARG) return fail(ctx, TAC_ERR_ARG, "cmux_rotate: unsupported level count for this parameter set");
-    TRY(rc);
+    TRY(check_launch(ctx, ctx->ops->cmux_test(klaunch(ctx), levels, ctx->ws_ggswf.as<cplx>(), ctx->ws_misc.as<int>(), base_log, n_acc, ctx->ws_out.as<uint64_t>()),
+                     "cmux_rotate_test_kernel"));
     CU(cudaMemcpyAsync(acc_host, ctx->ws_out.p, ab, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return TAC_OK;

@@ -1,19 +1,22 @@
 // ep_step.cuh — one CMux/external-product step for a CTA that owns B GLWE accumulators, as barrier-separated phases.
 //
 // Shared-memory objects (per CTA):
-//   acc   uint64  [B][G][N]     the B accumulators (G = k+1 polynomials each)
-//   S     cplx    [B*G][M]      one FFT buffer per (ciphertext, polynomial); reused for the MAC output
-//   twist cplx    [M]           e^{iπj/N}
-//   wM    cplx    [M]           e^{-2πie/M}
+//   acc   uint64  [B][G][N]       the B accumulators (G = k+1 polynomials each)
+//   S     cplx    [B*G][M]        one FFT buffer per (ciphertext, polynomial); reused for the MAC output
+//   dig   uint32  [B*G][L][M]     all decomposition digits of this step, samples (jj, jj+M) packed as biased u16 pairs
+//   wT    cplx    [M]             combined twist/twiddle table (ep_core.cuh)
 // Per-thread registers that live across the phases of one step: out[SPT][B][G] (Fourier-domain accumulators of the
 // frequency slots this thread owns).
 //
 // Phase order for one step (a barrier after every phase):
-//   for level = L .. 1:   fwd1(level)  fwd2  mac(level)
-//   outw  inv1  inv2
-// Both the CUDA kernels (kernels.cu) and the CPU emulation (tests/cpu/ep_emul.cpp) follow this order.
+//   decomp
+//   for level = L .. 1:   fwd1(level)  fwd2  mac(level)         (outw follows the last mac without a barrier)
+//   inv1  inv2
+// Both the CUDA kernels (kernels.cuh) and the CPU emulation (tests/cpu/ep_emul.cpp) follow this order.
 #pragma once
 #include "ep_core.cuh"
+
+#include <cmath>
 
 namespace tac {
 
@@ -28,6 +31,7 @@ struct EpCfg {
     static constexpr int N = N_, K = K_, L = L_, B = B_, G = K_ + 1, M = N_ / 2, JOBS = B_ * (K_ + 1);
     static constexpr size_t acc_words = (size_t)B_ * (K_ + 1) * N_;
     static constexpr size_t s_cplx = (size_t)B_ * (K_ + 1) * (N_ / 2);
+    static constexpr size_t dig_words = (size_t)B_ * (K_ + 1) * L_ * (N_ / 2);
 };
 constexpr int floor_pow2(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 template <class C, int NT>
@@ -36,17 +40,25 @@ struct MacCfg {
     static constexpr int SPT = C::M / NT_MAC;
 };
 
-// forward FFT pass 1 of the level-`lev` digits of (acc·X^rot − acc), one job per (ciphertext b, polynomial p)
-// rotf(b) returns the monomial degree (in [0, 2N)) applied to ciphertext b in this step
-template <class C, class RotFn>
-TAC_HD void ph_fwd1(int tid, int nt, int lev, const uint64_t* __restrict__ acc, RotFn rotf, const DecompF64& dc,
-                    const cplx* __restrict__ twist, const cplx* __restrict__ wM, cplx* __restrict__ S) {
+// Decompose every coefficient of the B·G operand polynomials into its L digits.  coef(job, j) returns coefficient j of
+// operand polynomial `job` (for a CMux with rotation: (acc·X^rot − acc)[j]).
+template <class C, class CoefFn>
+TAC_HD void ph_decomp(int tid, int nt, CoefFn coef, int base_log, uint32_t* __restrict__ dig) {
+    for (int idx = tid; idx < C::JOBS * C::M; idx += nt) {
+        const int job = idx / C::M, jj = idx - job * C::M;
+        uint32_t w[C::L];
+        decompose_pair<C::L>(coef(job, jj), coef(job, jj + C::M), base_log, w);
+#pragma unroll
+        for (int s = 0; s < C::L; s++) dig[((size_t)job * C::L + s) * C::M + jj] = w[s];
+    }
+}
+// forward FFT pass 1 of the level-`lev` digits, one job per (ciphertext b, polynomial p)
+template <class C>
+TAC_HD void ph_fwd1(int tid, int nt, int lev, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
     for (int job = grp; job < C::JOBS; job += ngrp) {
-        const uint64_t* poly = acc + (size_t)job * C::N;
-        const int r = rotf(job / C::G);
-        fft_fwd_pass1<C::N>(
-            t, [&](int j) { return digit_f64<C::L>(rot_diff<C::N>(poly, j, r), dc, lev); }, twist, wM, S + (size_t)job * C::M);
+        const uint32_t* d = dig + ((size_t)job * C::L + (lev - 1)) * C::M;
+        fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], a, b); }, wT, S + (size_t)job * C::M);
     }
 }
 template <class C>
@@ -63,20 +75,26 @@ TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* 
 #pragma unroll
     for (int it = 0; it < SPT; it++) {
         const int tau = tid + it * NT_MAC;
+        // software pipeline over the G rows: the key loads of row p+1 are in flight while row p is multiplied
+        cplx g[2][C::G];
+#pragma unroll
+        for (int c = 0; c < C::G; c++) g[0][c] = TAC_LDG(gl + (size_t)c * C::M + tau);
 #pragma unroll
         for (int p = 0; p < C::G; p++) {
-            cplx g[C::G];
+            if (p + 1 < C::G) {
 #pragma unroll
-            for (int c = 0; c < C::G; c++) g[c] = TAC_LDG(gl + (size_t)(p * C::G + c) * C::M + tau);
+                for (int c = 0; c < C::G; c++) g[(p + 1) & 1][c] = TAC_LDG(gl + (size_t)((p + 1) * C::G + c) * C::M + tau);
+            }
 #pragma unroll
             for (int b = 0; b < C::B; b++) {
                 const cplx x = S[(size_t)(b * C::G + p) * C::M + tau];
 #pragma unroll
-                for (int c = 0; c < C::G; c++) cfma(out[it][b][c], x, g[c]);
+                for (int c = 0; c < C::G; c++) cfma(out[it][b][c], x, g[p & 1][c]);
             }
         }
     }
 }
+// Written right after the last ph_mac without a barrier: a thread only reads and writes its own slots of S.
 template <class C, int NT_MAC, int SPT>
 TAC_HD void ph_outw(int tid, cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G]) {
     if (tid >= NT_MAC) return;
@@ -93,24 +111,41 @@ TAC_HD void ph_outw(int tid, cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G])
     }
 }
 template <class C>
-TAC_HD void ph_inv1(int tid, int nt, const cplx* __restrict__ wM, cplx* __restrict__ S) {
+TAC_HD void ph_inv1(int tid, int nt, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
-    for (int job = grp; job < C::JOBS; job += ngrp) fft_inv_passA<C::N>(t, wM, S + (size_t)job * C::M);
+    for (int job = grp; job < C::JOBS; job += ngrp) fft_inv_passA<C::N>(t, wT, S + (size_t)job * C::M);
 }
 template <class C>
-TAC_HD void ph_inv2(int tid, int nt, const cplx* __restrict__ twist, const cplx* __restrict__ S, uint64_t* __restrict__ acc) {
+TAC_HD void ph_inv2(int tid, int nt, const cplx* __restrict__ S, uint64_t* __restrict__ acc) {
     const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
     for (int job = grp; job < C::JOBS; job += ngrp) {
         uint64_t* poly = acc + (size_t)job * C::N;
-        fft_inv_passB<C::N>(t, twist, S + (size_t)job * C::M, 1.0, [&](int j, double v) { poly[j] += f64_to_torus(v); });
+        fft_inv_passB<C::N>(t, S + (size_t)job * C::M, [&](int jj, double re, double im) {
+            poly[jj] += f64_to_torus(re);
+            poly[jj + C::M] += f64_to_torus(im);
+        });
     }
 }
 
-// Fourier transform of a torus polynomial (keys): 16 threads, buffer S[M]; result left in S in slot order, scaled by `scale`.
+// Fourier transform of a torus polynomial (keys): 16 threads, buffer S[M]; result left in S in slot order, scaled by `scale`·2^-64.
 template <int N>
-TAC_HD void key_fft_pass1(int t, const uint64_t* __restrict__ poly, double scale, const cplx* __restrict__ twist,
-                          const cplx* __restrict__ wM, cplx* __restrict__ S) {
-    fft_fwd_pass1<N>(t, [&](int j) { return torus_to_f64(poly[j]) * scale; }, twist, wM, S);
+TAC_HD void key_fft_pass1(int t, const uint64_t* __restrict__ poly, double scale, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+    fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) {
+        a = torus_to_f64(poly[jj]) * scale;
+        b = torus_to_f64(poly[jj + N / 2]) * scale;
+    }, wT, S);
+}
+
+// host-side construction of the combined table in extended precision (capi.cu and the CPU emulation)
+inline void build_wT(int N, cplx* wT) {
+    const int M = N / 2, P = M / 16;
+    const long double pi = 3.141592653589793238462643383279502884L;
+    for (int q = 0; q < P; q++)
+        for (int t = 0; t < 16; t++) {
+            const long double ang = pi * t / N - 2.0L * pi * (long double)(t * q) / M;
+            cplx w; w.x = (double)cosl(ang); w.y = (double)sinl(ang);
+            wT[slot_of(q, t)] = w;
+        }
 }
 
 }  // namespace tac

@@ -1,0 +1,234 @@
+// kernels_ep.cuh — the FFT / external-product kernels (templated on the polynomial size and GLWE dimension):
+// poly_fft_kernel, pbs_kernel, vp_kernel, cmux_tree_kernel.  Instantiated per shape in kernels_n512.cu / kernels_n1024.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include "ep_step.cuh"
+
+namespace tac {
+
+template <int N> struct LogN { static constexpr int v = (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : -1; };
+
+// ================================================================================================ Fourier transform of torus polynomials
+// 16 polynomials per CTA (one per 16-thread group).  out[poly][M] in slot order, scaled by `scale`·2^-64.
+template <int N>
+__global__ void __launch_bounds__(256)
+poly_fft_kernel(const uint64_t* __restrict__ polys, size_t npoly, double scale, const cplx* __restrict__ g_wT, cplx* __restrict__ out) {
+    constexpr int M = N / 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* S = reinterpret_cast<cplx*>(smem_raw);
+    cplx* wT = S + 16 * M;
+    for (int i = threadIdx.x; i < M; i += 256) wT[i] = g_wT[i];
+    __syncthreads();
+    const int grp = threadIdx.x >> 4, t = threadIdx.x & 15;
+    const size_t poly = (size_t)blockIdx.x * 16 + grp;
+    if (poly < npoly) key_fft_pass1<N>(t, polys + poly * N, scale, wT, S + grp * M);
+    __syncthreads();
+    if (poly < npoly) fft_fwd_pass2<N>(t, S + grp * M);
+    __syncthreads();
+    const size_t base = (size_t)blockIdx.x * 16 * M;
+    const size_t lim = npoly * M;
+    for (int i = threadIdx.x; i < 16 * M; i += 256)
+        if (base + i < lim) out[base + i] = S[i];
+}
+
+// ================================================================================================ CMux chain plumbing
+template <class C>
+struct EpSmem {
+    uint64_t* acc; cplx* S; uint32_t* dig; cplx* wT; unsigned char* extra;
+    __device__ explicit EpSmem(unsigned char* raw) {
+        acc = reinterpret_cast<uint64_t*>(raw);
+        S = reinterpret_cast<cplx*>(acc + C::acc_words);
+        dig = reinterpret_cast<uint32_t*>(S + C::s_cplx);
+        wT = reinterpret_cast<cplx*>(dig + C::dig_words);
+        extra = reinterpret_cast<unsigned char*>(wT + C::M);
+    }
+    static constexpr size_t bytes = C::acc_words * 8 + C::s_cplx * 16 + C::dig_words * 4 + (size_t)C::M * 16;
+};
+
+// one step on the operand coef(job, j); the accumulators receive  acc += GGSW ⊡ operand
+template <class C, int NT, class CoefFn>
+__device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, const cplx* __restrict__ ggsw, CoefFn coef, int base_log,
+                                               cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G]) {
+    typedef MacCfg<C, NT> MC;
+    ph_decomp<C>(tid, NT, coef, base_log, sm.dig);
+    __syncthreads();
+#pragma unroll
+    for (int lev = C::L; lev >= 1; lev--) {
+        ph_fwd1<C>(tid, NT, lev, sm.dig, sm.wT, sm.S);
+        __syncthreads();
+        ph_fwd2<C>(tid, NT, sm.S);
+        __syncthreads();
+        ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, ggsw, sm.S, out);
+        if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);      // own slots only: no barrier needed in between
+        __syncthreads();
+    }
+    ph_inv1<C>(tid, NT, sm.wT, sm.S);
+    __syncthreads();
+    ph_inv2<C>(tid, NT, sm.S, sm.acc);
+    __syncthreads();
+}
+
+// [U] glwe_sample_extraction.rs::extract_lwe_sample_from_glwe_ciphertext(.., MonomialDegree(0)); element e of the LWE
+template <class C>
+__device__ __forceinline__ uint64_t sample_extract_elem(const uint64_t* __restrict__ glwe, int e) {
+    if (e == C::K * C::N) return glwe[(size_t)C::K * C::N];
+    const int p = e / C::N, j = e - p * C::N;
+    const uint64_t* a = glwe + (size_t)p * C::N;
+    return (j == 0) ? a[0] : (0ull - a[C::N - j]);
+}
+
+// ================================================================================================ PBS (homomorphic_shift_boolean)
+// in: small LWE [nct][n+1]; out: big LWE [nct][kN+1] encrypting bit·2·alpha.
+// [U] wop_pbs.rs::homomorphic_shift_boolean + bootstrap.rs::{blind_rotate_assign, bootstrap}
+template <int N, int K, int L, int B, int NT>
+__global__ void __launch_bounds__(NT, 1)
+pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
+           const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
+    typedef EpCfg<N, K, L, B> C;
+    typedef MacCfg<C, NT> MC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EpSmem<C> sm(smem_raw);
+    int* rot_sm = reinterpret_cast<int*>(sm.extra);               // [2][B] monomial degree of the current / next step
+    const int tid = threadIdx.x;
+    const int ct0 = blockIdx.x * B;
+    const int n1 = n + 1;
+    // modulus-switched element i of ciphertext b (0 for the padding ciphertexts of the last CTA)
+    auto switched = [&](int b, int i) -> int {
+        const int ct = ct0 + b;
+        if (ct >= nct) return 0;
+        uint64_t a = __ldg(lwe_small + (size_t)ct * n1 + i);
+        if (i == n) a += (1ull << 62);                             // centre the error for the negacyclic LUT
+        return modswitch(a, LogN<N>::v);
+    };
+    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    if (tid < B) { rot_sm[tid] = switched(tid, 0); rot_sm[B + tid] = switched(tid, n); }
+    __syncthreads();
+    // accumulator = trivial GLWE(-alpha in every coefficient) · X^{-b~}
+    for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
+        const int b = idx / (C::G * N), rem = idx - b * C::G * N, p = rem / N, j = rem - p * N;
+        uint64_t v = 0;
+        if (p == K) {
+            const int s = (j + rot_sm[B + b]) & (2 * N - 1);
+            v = (s < N) ? (0ull - alpha) : alpha;
+        }
+        sm.acc[idx] = v;
+    }
+    __syncthreads();
+    cplx out[MC::SPT][B][C::G];
+#pragma unroll
+    for (int a = 0; a < MC::SPT; a++)
+#pragma unroll
+        for (int b = 0; b < B; b++)
+#pragma unroll
+            for (int c = 0; c < C::G; c++) out[a][b][c] = mk(0.0, 0.0);
+    const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    for (int i = 0; i < n; i++) {
+        const int* rot = rot_sm + (i & 1) * B;
+        if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+        ep_step_device<C, NT>(tid, sm, bsk + ggsw_sz * i,
+                              [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, out);
+    }
+    constexpr int LW = K * N + 1;
+    for (int idx = tid; idx < B * LW; idx += NT) {
+        const int b = idx / LW, e = idx - b * LW, ct = ct0 + b;
+        if (ct >= nct) continue;
+        uint64_t v = sample_extract_elem<C>(sm.acc + (size_t)b * C::G * N, e);
+        if (e == K * N) v += alpha;
+        out_big[(size_t)ct * LW + e] = v;
+    }
+}
+
+// ================================================================================================ vertical packing
+// One CTA evaluates B outputs of one box (= one circuit_bootstrap call).  ggsw_f: [nbox][n_in][L][G][G][M].
+// The accumulator starts from init_glwe (CMux-tree result) when given, else from the trivial GLWE of LUT polynomial o.
+// Blind rotation uses GGSWs n_in-1 … first_ggsw with X^{-1}, X^{-2}, X^{-4}, …   ([U] wop_pbs.rs::{vertical_packing, blind_rotate_assign})
+template <int N, int K, int L, int B, int NT>
+__global__ void __launch_bounds__(NT, 1)
+vp_kernel(const cplx* __restrict__ ggsw_f, int n_in, int first_ggsw, const uint64_t* __restrict__ lut, size_t lut_stride,
+          const uint64_t* __restrict__ init_glwe, int n_out, int base_log, const cplx* __restrict__ g_wT, uint64_t* __restrict__ out) {
+    typedef EpCfg<N, K, L, B> C;
+    typedef MacCfg<C, NT> MC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EpSmem<C> sm(smem_raw);
+    const int tid = threadIdx.x;
+    const int box = blockIdx.y, o0 = blockIdx.x * B;
+    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
+        const int b = idx / (C::G * N), rem = idx - b * C::G * N, p = rem / N, j = rem - p * N;
+        const int o = o0 + b;
+        uint64_t v = 0;
+        if (o < n_out) {
+            if (init_glwe) v = init_glwe[((size_t)box * n_out + o) * C::G * N + rem];
+            else if (p == K) v = lut[(size_t)o * lut_stride + j];
+        }
+        sm.acc[idx] = v;
+    }
+    __syncthreads();
+    cplx outr[MC::SPT][B][C::G];
+#pragma unroll
+    for (int a = 0; a < MC::SPT; a++)
+#pragma unroll
+        for (int b = 0; b < B; b++)
+#pragma unroll
+            for (int c = 0; c < C::G; c++) outr[a][b][c] = mk(0.0, 0.0);
+    const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    const cplx* gbox = ggsw_f + (size_t)box * n_in * ggsw_sz;
+    int deg = 1;
+    for (int g = n_in - 1; g >= first_ggsw; g--) {
+        const int rot = 2 * N - deg;            // multiply by X^{-deg}
+        ep_step_device<C, NT>(tid, sm, gbox + (size_t)g * ggsw_sz,
+                              [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot); }, base_log, outr);
+        deg <<= 1;
+    }
+    constexpr int LW = K * N + 1;
+    for (int idx = tid; idx < B * LW; idx += NT) {
+        const int b = idx / LW, e = idx - b * LW, o = o0 + b;
+        if (o >= n_out) continue;
+        out[((size_t)box * n_out + o) * LW + e] = sample_extract_elem<C>(sm.acc + (size_t)b * C::G * N, e);
+    }
+}
+
+// One CMux-tree layer ([U] wop_pbs.rs::cmux_tree_memory_optimized, evaluated level by level): for every (box, output,
+// pair i): node_out[i] = c0 + G ⊡ (c1 − c0) with c0 = node_in[2i], c1 = node_in[2i+1].  leaf != 0: inputs are LUT
+// polynomials (trivial GLWEs).  Implemented with the rotation step on a doubled trick: acc = c0, "rot" disabled — the
+// difference c1 − c0 is written to a scratch accumulator instead.  One CTA per node (B = 1).
+template <int N, int K, int L, int NT>
+__global__ void __launch_bounds__(NT, 1)
+cmux_tree_kernel(const cplx* __restrict__ ggsw_f, int n_in, int ggsw_idx, const uint64_t* __restrict__ lut, size_t lut_stride,
+                 const uint64_t* __restrict__ node_in, int n_nodes_in, int n_out, int base_log, const cplx* __restrict__ g_wT,
+                 uint64_t* __restrict__ node_out) {
+    typedef EpCfg<N, K, L, 1> C;
+    typedef MacCfg<C, NT> MC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EpSmem<C> sm(smem_raw);
+    uint64_t* diff = reinterpret_cast<uint64_t*>(sm.extra);       // [G][N]  c1 − c0
+    const int tid = threadIdx.x;
+    const int pair = blockIdx.x, o = blockIdx.y, box = blockIdx.z;
+    const int n_pairs = n_nodes_in / 2;
+    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int idx = tid; idx < C::G * N; idx += NT) {
+        uint64_t c0, c1;
+        if (node_in) {
+            const uint64_t* base = node_in + (((size_t)box * n_out + o) * n_nodes_in + 2 * pair) * C::G * N;
+            c0 = base[idx]; c1 = base[(size_t)C::G * N + idx];
+        } else {
+            const int p = idx / N, j = idx - p * N;
+            const uint64_t* lp = lut + (size_t)o * lut_stride + (size_t)(2 * pair) * N;
+            c0 = (p == K) ? lp[j] : 0ull; c1 = (p == K) ? lp[N + j] : 0ull;
+        }
+        sm.acc[idx] = c0; diff[idx] = c1 - c0;
+    }
+    __syncthreads();
+    cplx outr[MC::SPT][1][C::G];
+#pragma unroll
+    for (int a = 0; a < MC::SPT; a++)
+#pragma unroll
+        for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
+    const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    const cplx* ggsw = ggsw_f + ((size_t)box * n_in + ggsw_idx) * ggsw_sz;
+    ep_step_device<C, NT>(tid, sm, ggsw, [&](int job, int j) { return diff[(size_t)job * N + j]; }, base_log, outr);
+    uint64_t* dst = node_out + (((size_t)box * n_out + o) * n_pairs + pair) * C::G * N;
+    for (int idx = tid; idx < C::G * N; idx += NT) dst[idx] = sm.acc[idx];
+}
+
+}  // namespace tac

@@ -1,0 +1,124 @@
+// kernels_shape.inl — instantiates the EP kernels for one shape.  The including .cu defines TAC_N, TAC_K, TAC_SHAPE_FN and
+// the list of PBS level counts via TAC_PBS_LEVELS(X).
+#include "kernels_ep.cuh"
+#include "shape_launch.h"
+
+namespace tac {
+namespace {
+
+constexpr int SN = TAC_N, SK = TAC_K;
+
+#define TAC_SET_SMEM(kern, bytes)                                                                      \
+    do {                                                                                               \
+        cudaError_t e__ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)); \
+        if (e__ != cudaSuccess) return e__;                                                            \
+    } while (0)
+
+cudaError_t s_poly_fft(const KLaunch& k, const uint64_t* polys, size_t npoly, double scale, double2* out) {
+    constexpr int M = SN / 2;
+    const size_t smem = (size_t)(16 * M + M) * sizeof(cplx);
+    TAC_SET_SMEM(poly_fft_kernel<SN>, smem);
+    poly_fft_kernel<SN><<<(unsigned)((npoly + 15) / 16), 256, smem, k.stream>>>(polys, npoly, scale, k.wT, out);
+    return cudaGetLastError();
+}
+
+template <int L, int B, int NT>
+cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
+    typedef EpCfg<SN, SK, L, B> C;
+    const size_t smem = EpSmem<C>::bytes + 2 * B * sizeof(int);
+    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT>), smem);
+    pbs_kernel<SN, SK, L, B, NT><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    return cudaGetLastError();
+}
+template <int L>
+cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
+#if TAC_N == 512
+    // B ciphertexts per CTA share every BSK load; fewer per CTA when the batch cannot fill the GPU otherwise
+    if (nct >= 4 * k.sm_count) return launch_pbs<L, 4, 320>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 160>(k, small, nct, n, bsk, base_log, alpha, out);
+    return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);
+#else
+    return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation
+#endif
+}
+cudaError_t s_pbs(const KLaunch& k, int levels, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
+#define X(LV) if (levels == LV) return pbs_levels<LV>(k, small, nct, n, bsk, base_log, alpha, out);
+    TAC_PBS_LEVELS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+template <int B, int NT>
+cudaError_t launch_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+                      const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
+    typedef EpCfg<SN, SK, 1, B> C;
+    const size_t smem = EpSmem<C>::bytes;
+    TAC_SET_SMEM((vp_kernel<SN, SK, 1, B, NT>), smem);
+    dim3 grid((n_out + B - 1) / B, nbox);
+    vp_kernel<SN, SK, 1, B, NT><<<grid, NT, smem, k.stream>>>(ggsw_f, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, k.wT, out);
+    return cudaGetLastError();
+}
+cudaError_t s_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+                 const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
+#if TAC_N == 512
+    if (n_out >= 4) return launch_vp<4, 320>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+#endif
+    return launch_vp<1, 128>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+}
+
+cudaError_t s_tree(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
+                   const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
+    typedef EpCfg<SN, SK, 1, 1> C;
+    const size_t smem = EpSmem<C>::bytes + (size_t)C::G * SN * sizeof(uint64_t);
+    TAC_SET_SMEM((cmux_tree_kernel<SN, SK, 1, 128>), smem);
+    dim3 grid(n_nodes_in / 2, n_out, nbox);
+    cmux_tree_kernel<SN, SK, 1, 128><<<grid, 128, smem, k.stream>>>(ggsw_f, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log, k.wT, node_out);
+    return cudaGetLastError();
+}
+
+// one CMux-with-rotation step per accumulator (B = 1 CTA each) — test entry point for the FFT / external-product core
+template <int L, int NT>
+__global__ void __launch_bounds__(NT, 1)
+cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__ rot, int base_log, const cplx* __restrict__ g_wT,
+                        uint64_t* __restrict__ acc_io) {
+    typedef EpCfg<SN, SK, L, 1> C;
+    typedef MacCfg<C, NT> MC;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    EpSmem<C> sm(smem_raw);
+    const int tid = threadIdx.x;
+    uint64_t* g = acc_io + (size_t)blockIdx.x * C::G * SN;
+    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int i = tid; i < C::G * SN; i += NT) sm.acc[i] = g[i];
+    __syncthreads();
+    cplx outr[MC::SPT][1][C::G];
+#pragma unroll
+    for (int a = 0; a < MC::SPT; a++)
+#pragma unroll
+        for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
+    const int r = rot[blockIdx.x];
+    ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int job, int j) { return rot_diff<SN>(sm.acc + (size_t)job * SN, j, r); }, base_log, outr);
+    for (int i = tid; i < C::G * SN; i += NT) g[i] = sm.acc[i];
+}
+template <int L>
+cudaError_t launch_cmux_test(const KLaunch& k, const double2* gf, const int* rot, int base_log, int n_acc, uint64_t* acc) {
+    typedef EpCfg<SN, SK, L, 1> C;
+    const size_t smem = EpSmem<C>::bytes;
+    TAC_SET_SMEM((cmux_rotate_test_kernel<L, 128>), smem);
+    cmux_rotate_test_kernel<L, 128><<<n_acc, 128, smem, k.stream>>>(gf, rot, base_log, k.wT, acc);
+    return cudaGetLastError();
+}
+cudaError_t s_cmux_test(const KLaunch& k, int levels, const double2* gf, const int* rot, int base_log, int n_acc, uint64_t* acc) {
+    if (levels == 1) return launch_cmux_test<1>(k, gf, rot, base_log, n_acc, acc);
+#define X(LV) if (levels == LV) return launch_cmux_test<LV>(k, gf, rot, base_log, n_acc, acc);
+    TAC_PBS_LEVELS(X)
+#undef X
+    return cudaErrorInvalidValue;
+}
+
+const ShapeOps kOps = {SN, SK, s_poly_fft, s_pbs, s_vp, s_tree, s_cmux_test};
+
+}  // namespace
+
+const ShapeOps* TAC_SHAPE_FN() { return &kOps; }
+
+}  // namespace tac

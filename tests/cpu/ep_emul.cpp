@@ -21,21 +21,29 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
         for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, buf.data());
         for (int s = 0; s < C::M; s++) gf[(size_t)q * C::M + s] = buf[s];
     }
-    struct Regs { cplx v[MC::SPT][C::B][C::G]; };
+    struct Regs { cplx v[MC::SPT][C::B][C::G]; cplx g[MAC_DEPTH][C::G]; };
     std::vector<Regs> regs(NT);
     for (auto& r : regs) for (int a = 0; a < MC::SPT; a++) for (int b = 0; b < C::B; b++) for (int c = 0; c < C::G; c++) r.v[a][b][c] = mk(0, 0);
     std::vector<cplx> S(C::s_cplx);
-    std::vector<uint32_t> dig(C::dig_words);
-    auto coef = [&](int job, int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); };
-    for (int tid = 0; tid < NT; tid++) ph_decomp<C>(tid, NT, coef, base_log, dig.data());
-    for (int lev = L; lev >= 1; lev--) {
-        for (int tid = 0; tid < NT; tid++) ph_fwd1<C>(tid, NT, lev, dig.data(), wT.data(), S.data());
-        for (int tid = 0; tid < NT; tid++) ph_fwd2<C>(tid, NT, S.data());
-        for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, gf.data(), S.data(), regs[tid].v);
+    std::vector<uint32_t> dig(C::dig_words + 1);
+    // phase order of ep_step_device (kernels_ep.cuh); a group-local __syncwarp() is modelled by finishing a pass for all
+    // threads before the next pass starts
+    auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < C::JOBS) fn(t, job); } };
+    groups([&](int t, int job) {
+        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, dig.data(), wT.data(), S.data());
+    });
+    groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
+    for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC>(tid, L, gf.data(), regs[tid].g);
+    for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, L, gf.data(), S.data(), regs[tid].v, regs[tid].g);
+    for (int lev = L - 1; lev >= 1; lev--) {
+        groups([&](int t, int job) { grp_fwd1<C>(t, job, lev, dig.data(), wT.data(), S.data()); });
+        groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
+        for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, gf.data(), regs[tid].g);
+        for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, gf.data(), S.data(), regs[tid].v, regs[tid].g);
     }
     for (int tid = 0; tid < NT; tid++) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, S.data(), regs[tid].v);
-    for (int tid = 0; tid < NT; tid++) ph_inv1<C>(tid, NT, wT.data(), S.data());
-    for (int tid = 0; tid < NT; tid++) ph_inv2<C>(tid, NT, S.data(), acc);
+    groups([&](int t, int job) { grp_inv1<C>(t, job, wT.data(), S.data()); });
+    groups([&](int t, int job) { grp_inv2<C>(t, job, S.data(), acc); });
 }
 
 // forward transform of a real polynomial given as doubles; returns slot-ordered spectrum + the frequency held by each slot

@@ -3,6 +3,7 @@
 // no usable CUDA device.
 #include "../../include/tfhe_aes_cuda.h"
 #include "kernels_common.cuh"
+#include "kernels_pfks_tc.cuh"
 #include "ep_step.cuh"
 #include "shape_launch.h"
 
@@ -47,6 +48,8 @@ struct tac_ctx {
     uint64_t* pfpksk = nullptr;
     uint64_t* ks_corr = nullptr;
     uint64_t* pfks_corr = nullptr;
+    uint8_t* pfks_planes = nullptr;      // byte planes of the PFPKSK for the tensor-core GEMM (kernels_pfks_tc.cuh)
+    uint32_t* pfks_fix = nullptr;        // [0] = count, then uint2 (ct, k) entries
     bool keys_allocated = false, keys_valid = false;
     // tables
     cplx* wT = nullptr;            // combined twist/twiddle table (ep_core.cuh)
@@ -196,14 +199,29 @@ int stage_ks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* small) {
     TRY(post_launch(ctx, "ks_digits_kernel"));
     return gemm(ctx, ctx->ws_ksdig.as<uint32_t>(), nct, Kd, ctx->ksk, p.n + 1, 1, ctx->ks_corr, in + big, (size_t)big + 1, small);
 }
-// PFKS with all k+1 keys: in [nct][big+1] → ggsw_std [nct][G][G·N]
+// PFKS with all k+1 keys on the tensor cores: in [nct][big+1] → ggsw_std [nct][G][G·N]
+constexpr uint32_t kFixCap = 1u << 16;
 int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     const TacParams& p = ctx->p;
-    const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l;
-    TRY(ensure(ctx, ctx->ws_pfdig, (size_t)nct * Kd * 4));
-    pfks_digits_kernel<<<grid1d((size_t)nct * big1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big1, p.pfks_b, p.pfks_l, ctx->ws_pfdig.as<uint32_t>());
-    TRY(post_launch(ctx, "pfks_digits_kernel"));
-    return gemm(ctx, ctx->ws_pfdig.as<uint32_t>(), nct, Kd, ctx->pfpksk, ctx->G() * p.N, ctx->G(), ctx->pfks_corr, nullptr, 0, ggsw);
+    const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
+    const int W = ctx->G() * p.N, mpad = ((nct + TC_MT - 1) / TC_MT) * TC_MT;
+    if (p.pfks_b > 16) {       // digits wider than 16 bits (params_sqrd_lvl_1: base 2^24): 64-bit integer-pipe GEMM
+        TRY(ensure(ctx, ctx->ws_pfdig, (size_t)nct * Kd * 4));
+        pfks_digits_kernel<<<grid1d((size_t)nct * big1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big1, p.pfks_b, p.pfks_l, ctx->ws_pfdig.as<uint32_t>());
+        TRY(post_launch(ctx, "pfks_digits_kernel"));
+        return gemm(ctx, ctx->ws_pfdig.as<uint32_t>(), nct, Kd, ctx->pfpksk, W, ctx->G(), ctx->pfks_corr, nullptr, 0, ggsw);
+    }
+    TRY(ensure(ctx, ctx->ws_pfdig, (size_t)2 * nkb * 2 * mpad * 16));
+    CU(cudaMemsetAsync(ctx->pfks_fix, 0, 4, ctx->stream));
+    uint8_t* DA = ctx->ws_pfdig.as<uint8_t>();
+    pfks_digits_tc_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), kFixCap);
+    TRY(post_launch(ctx, "pfks_digits_tc_kernel"));
+    dim3 grid(ctx->G() * (W / TC_NT), mpad / TC_MT);
+    pfks_gemm_tc_kernel<<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, ggsw);
+    TRY(post_launch(ctx, "pfks_gemm_tc_kernel"));
+    pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), kFixCap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
+    return post_launch(ctx, "pfks_fixup_kernel");
 }
 
 // the whole circuit bootstrap for `nbox` boxes resident on the device
@@ -325,7 +343,7 @@ void tac_ctx_destroy(tac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->wT,
+    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->pfks_planes, (void*)ctx->pfks_fix, (void*)ctx->wT,
                     (void*)ctx->key_sched})
         if (p) cudaFree(p);
     for (auto& l : ctx->luts) cudaFree(l.dev);
@@ -394,6 +412,11 @@ int tac_ctx_alloc_keys(tac_ctx* ctx) {
     CU(cudaMalloc(&ctx->pfpksk, ctx->pfpksk_words() * 8));
     CU(cudaMalloc(&ctx->ks_corr, (size_t)(ctx->p.n + 1) * 8));
     CU(cudaMalloc(&ctx->pfks_corr, (size_t)ctx->G() * ctx->G() * ctx->p.N * 8));
+    {
+        const int Kd = (ctx->big() + 1) * ctx->p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
+        CU(cudaMalloc(&ctx->pfks_planes, (size_t)ctx->G() * nkb * TC_KB * ctx->G() * ctx->p.N * 8));
+        CU(cudaMalloc(&ctx->pfks_fix, 8 + (size_t)kFixCap * 8));
+    }
     ctx->keys_allocated = true;
     return TAC_OK;
 }
@@ -428,6 +451,13 @@ int tac_ctx_keys_ready(tac_ctx* ctx) {
     negate_kernel<<<grid1d(W * ctx->G(), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfks_corr, W * ctx->G());
     TRY(post_launch(ctx, "negate_kernel"));
     CU(cudaStreamSynchronize(ctx->stream));
+    {   // byte planes of the PFPKSK for the tensor-core GEMM
+        const int nkb = (Kd_pf + TC_KB - 1) / TC_KB;
+        const size_t units = (size_t)ctx->G() * nkb * (W / TC_NT) * 2 * TC_NT;
+        pfks_key_planes_kernel<<<grid1d(units, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfpksk, ctx->G(), Kd_pf, (int)W, nkb, ctx->pfks_planes);
+        TRY(post_launch(ctx, "pfks_key_planes_kernel"));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->keys_valid = true;
     return TAC_OK;
 }

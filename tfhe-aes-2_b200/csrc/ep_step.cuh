@@ -3,16 +3,21 @@
 // Shared-memory objects (per CTA):
 //   acc   uint64  [B][G][N]       the B accumulators (G = k+1 polynomials each)
 //   S     cplx    [B*G][M]        one FFT buffer per (ciphertext, polynomial); reused for the MAC output
-//   dig   uint32  [B*G][L][M]     all decomposition digits of this step, samples (jj, jj+M) packed as biased u16 pairs
+//   dig   uint32  [B*G][L-1][M]   decomposition digits of levels 1..L-1 of this step (level L is consumed at once),
+//                                 samples (jj, jj+M) packed as biased u16 pairs
 //   wT    cplx    [M]             combined twist/twiddle table (ep_core.cuh)
 // Per-thread registers that live across the phases of one step: out[SPT][B][G] (Fourier-domain accumulators of the
 // frequency slots this thread owns).
 //
-// Phase order for one step (a barrier after every phase):
-//   decomp
-//   for level = L .. 1:   fwd1(level)  fwd2  mac(level)         (outw follows the last mac without a barrier)
-//   inv1  inv2
-// Both the CUDA kernels (kernels.cuh) and the CPU emulation (tests/cpu/ep_emul.cpp) follow this order.
+// Work split: one 16-thread group (half a warp) owns one operand polynomial "job" = (ciphertext b, polynomial p): it
+// decomposes it, runs its forward FFTs, later its inverse FFT and the accumulator update.  All of that touches only the
+// group's own rows of acc / dig / S, so inside a group a __syncwarp() orders the passes.  Only the Fourier-domain
+// multiply-accumulate crosses groups (thread τ reads slot τ of every job), so a step needs just two CTA barriers per level:
+//
+//   group:  decomp + fwd1(L) | fwd2        ── barrier ──  all: mac(L)     ── barrier ──
+//   group:  fwd1(l) | fwd2                 ── barrier ──  all: mac(l)     ── barrier ──      l = L-1 … 1   (mac(1) also writes out)
+//   group:  inv1 | inv2 |                                                                     ( | = __syncwarp )
+// Both the CUDA kernels (kernels_ep.cuh) and the CPU emulation (tests/cpu/ep_emul.cpp) follow this order.
 #pragma once
 #include "ep_core.cuh"
 
@@ -31,7 +36,7 @@ struct EpCfg {
     static constexpr int N = N_, K = K_, L = L_, B = B_, G = K_ + 1, M = N_ / 2, JOBS = B_ * (K_ + 1);
     static constexpr size_t acc_words = (size_t)B_ * (K_ + 1) * N_;
     static constexpr size_t s_cplx = (size_t)B_ * (K_ + 1) * (N_ / 2);
-    static constexpr size_t dig_words = (size_t)B_ * (K_ + 1) * L_ * (N_ / 2);
+    static constexpr size_t dig_words = (size_t)B_ * (K_ + 1) * (L_ > 1 ? L_ - 1 : 0) * (N_ / 2);
 };
 constexpr int floor_pow2(int x) { int p = 1; while (p * 2 <= x) p *= 2; return p; }
 template <class C, int NT>
@@ -40,57 +45,66 @@ struct MacCfg {
     static constexpr int SPT = C::M / NT_MAC;
 };
 
-// Decompose every coefficient of the B·G operand polynomials into its L digits.  coef(job, j) returns coefficient j of
-// operand polynomial `job` (for a CMux with rotation: (acc·X^rot − acc)[j]).
+// group phase 1 of a step: decompose the operand polynomial `job` (coef(j) = its coefficient j), keep the digits of
+// levels 1..L-1 in dig, and run forward-FFT pass 1 on the level-L digits straight from registers.
 template <class C, class CoefFn>
-TAC_HD void ph_decomp(int tid, int nt, CoefFn coef, int base_log, uint32_t* __restrict__ dig) {
-    for (int idx = tid; idx < C::JOBS * C::M; idx += nt) {
-        const int job = idx / C::M, jj = idx - job * C::M;
+TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, int base_log, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
+                            cplx* __restrict__ S) {
+    uint32_t* dj = dig + (size_t)job * (C::L - 1) * C::M;
+    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) {
         uint32_t w[C::L];
-        decompose_pair<C::L>(coef(job, jj), coef(job, jj + C::M), base_log, w);
+        decompose_pair<C::L>(coef(jj), coef(jj + C::M), base_log, w);
 #pragma unroll
-        for (int s = 0; s < C::L; s++) dig[((size_t)job * C::L + s) * C::M + jj] = w[s];
-    }
+        for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
+        unpack_digits(w[C::L - 1], a, b);
+    }, wT, S + (size_t)job * C::M);
 }
-// forward FFT pass 1 of the level-`lev` digits, one job per (ciphertext b, polynomial p)
+// forward FFT pass 1 of the cached level-`lev` digits (lev < L)
 template <class C>
-TAC_HD void ph_fwd1(int tid, int nt, int lev, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
-    const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
-    for (int job = grp; job < C::JOBS; job += ngrp) {
-        const uint32_t* d = dig + ((size_t)job * C::L + (lev - 1)) * C::M;
-        fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], a, b); }, wT, S + (size_t)job * C::M);
-    }
+TAC_HD void grp_fwd1(int t, int job, int lev, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+    const uint32_t* d = dig + ((size_t)job * (C::L - 1) + (lev - 1)) * C::M;
+    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], a, b); }, wT, S + (size_t)job * C::M);
 }
 template <class C>
-TAC_HD void ph_fwd2(int tid, int nt, cplx* __restrict__ S) {
-    const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
-    for (int job = grp; job < C::JOBS; job += ngrp) fft_fwd_pass2<C::N>(t, S + (size_t)job * C::M);
-}
+TAC_HD void grp_fwd2(int t, int job, cplx* __restrict__ S) { fft_fwd_pass2<C::N>(t, S + (size_t)job * C::M); }
 // out[b][c] += Σ_p fft(digits_{lev,p} of ct b) · GGSW[lev-1][p][c]   at the slots owned by this thread.
 // ggsw: Fourier GGSW of this step, [L][G][G][M] slot-ordered (already scaled by 2^-64 / M).
+// Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that
+// precedes the MAC (the L2 latency hides behind the barrier wait), row p+MAC_DEPTH is requested while row p is multiplied.
+constexpr int MAC_DEPTH = 3;
+template <class C, int NT_MAC>
+TAC_HD void mac_load_row(const cplx* __restrict__ gl, int p, int tau, cplx (&dst)[C::G]) {
+#pragma unroll
+    for (int c = 0; c < C::G; c++) dst[c] = TAC_LDG(gl + (size_t)(p * C::G + c) * C::M + tau);
+}
+template <class C, int NT_MAC>
+TAC_HD void ph_mac_prefetch(int tid, int lev, const cplx* __restrict__ ggsw, cplx (&g)[MAC_DEPTH][C::G]) {
+    if (tid >= NT_MAC) return;
+    const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
+#pragma unroll
+    for (int p = 0; p < MAC_DEPTH && p < C::G; p++) mac_load_row<C, NT_MAC>(gl, p, tid, g[p]);
+}
 template <class C, int NT_MAC, int SPT>
-TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G]) {
+TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G],
+                   cplx (&g)[MAC_DEPTH][C::G]) {
     if (tid >= NT_MAC) return;
     const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
 #pragma unroll
     for (int it = 0; it < SPT; it++) {
         const int tau = tid + it * NT_MAC;
-        // software pipeline over the G rows: the key loads of row p+1 are in flight while row p is multiplied
-        cplx g[2][C::G];
+        if (it > 0) {
 #pragma unroll
-        for (int c = 0; c < C::G; c++) g[0][c] = TAC_LDG(gl + (size_t)c * C::M + tau);
+            for (int p = 0; p < MAC_DEPTH && p < C::G; p++) mac_load_row<C, NT_MAC>(gl, p, tau, g[p]);
+        }
 #pragma unroll
         for (int p = 0; p < C::G; p++) {
-            if (p + 1 < C::G) {
-#pragma unroll
-                for (int c = 0; c < C::G; c++) g[(p + 1) & 1][c] = TAC_LDG(gl + (size_t)((p + 1) * C::G + c) * C::M + tau);
-            }
 #pragma unroll
             for (int b = 0; b < C::B; b++) {
                 const cplx x = S[(size_t)(b * C::G + p) * C::M + tau];
 #pragma unroll
-                for (int c = 0; c < C::G; c++) cfma(out[it][b][c], x, g[p & 1][c]);
+                for (int c = 0; c < C::G; c++) cfma(out[it][b][c], x, g[p % MAC_DEPTH][c]);
             }
+            if (p + MAC_DEPTH < C::G) mac_load_row<C, NT_MAC>(gl, p + MAC_DEPTH, tau, g[p % MAC_DEPTH]);
         }
     }
 }
@@ -111,20 +125,14 @@ TAC_HD void ph_outw(int tid, cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G])
     }
 }
 template <class C>
-TAC_HD void ph_inv1(int tid, int nt, const cplx* __restrict__ wT, cplx* __restrict__ S) {
-    const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
-    for (int job = grp; job < C::JOBS; job += ngrp) fft_inv_passA<C::N>(t, wT, S + (size_t)job * C::M);
-}
+TAC_HD void grp_inv1(int t, int job, const cplx* __restrict__ wT, cplx* __restrict__ S) { fft_inv_passA<C::N>(t, wT, S + (size_t)job * C::M); }
 template <class C>
-TAC_HD void ph_inv2(int tid, int nt, const cplx* __restrict__ S, uint64_t* __restrict__ acc) {
-    const int grp = tid >> 4, t = tid & 15, ngrp = nt >> 4;
-    for (int job = grp; job < C::JOBS; job += ngrp) {
-        uint64_t* poly = acc + (size_t)job * C::N;
-        fft_inv_passB<C::N>(t, S + (size_t)job * C::M, [&](int jj, double re, double im) {
-            poly[jj] += f64_to_torus(re);
-            poly[jj + C::M] += f64_to_torus(im);
-        });
-    }
+TAC_HD void grp_inv2(int t, int job, const cplx* __restrict__ S, uint64_t* __restrict__ acc) {
+    uint64_t* poly = acc + (size_t)job * C::N;
+    fft_inv_passB<C::N>(t, S + (size_t)job * C::M, [&](int jj, double re, double im) {
+        poly[jj] += f64_to_torus(re);
+        poly[jj + C::M] += f64_to_torus(im);
+    });
 }
 
 // Fourier transform of a torus polynomial (keys): 16 threads, buffer S[M]; result left in S in slot order, scaled by `scale`·2^-64.

@@ -45,27 +45,40 @@ struct EpSmem {
     static constexpr size_t bytes = C::acc_words * 8 + C::s_cplx * 16 + C::dig_words * 4 + (size_t)C::M * 16;
 };
 
-// one step on the operand coef(job, j); the accumulators receive  acc += GGSW ⊡ operand
+// one step on the operand coef(job, j); the accumulators receive  acc += GGSW ⊡ operand.
+// Ends with a __syncwarp(): the accumulator rows of a job are only touched by the job's own 16-thread group, so the next
+// step's decomposition may follow without a CTA barrier.  (Readers of acc from other groups must __syncthreads() first.)
 template <class C, int NT, class CoefFn>
 __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, const cplx* __restrict__ ggsw, CoefFn coef, int base_log,
                                                cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G]) {
     typedef MacCfg<C, NT> MC;
-    ph_decomp<C>(tid, NT, coef, base_log, sm.dig);
+    static_assert(NT / 16 >= C::JOBS, "one 16-thread group per operand polynomial");
+    const int job = tid >> 4, t = tid & 15;
+    const bool active = job < C::JOBS;
+    cplx g[MAC_DEPTH][C::G];            // key prefetch ring (ep_step.cuh)
+    if (active) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, base_log, sm.dig, sm.wT, sm.S);
+    __syncwarp();
+    if (active) grp_fwd2<C>(t, job, sm.S);
+    ph_mac_prefetch<C, MC::NT_MAC>(tid, C::L, ggsw, g);
+    __syncthreads();
+    ph_mac<C, MC::NT_MAC, MC::SPT>(tid, C::L, ggsw, sm.S, out, g);
+    if (C::L == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);         // own slots only: no barrier needed in between
     __syncthreads();
 #pragma unroll
-    for (int lev = C::L; lev >= 1; lev--) {
-        ph_fwd1<C>(tid, NT, lev, sm.dig, sm.wT, sm.S);
+    for (int lev = C::L - 1; lev >= 1; lev--) {
+        if (active) grp_fwd1<C>(t, job, lev, sm.dig, sm.wT, sm.S);
+        __syncwarp();
+        if (active) grp_fwd2<C>(t, job, sm.S);
+        ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, ggsw, g);
         __syncthreads();
-        ph_fwd2<C>(tid, NT, sm.S);
-        __syncthreads();
-        ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, ggsw, sm.S, out);
-        if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);      // own slots only: no barrier needed in between
+        ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, ggsw, sm.S, out, g);
+        if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);
         __syncthreads();
     }
-    ph_inv1<C>(tid, NT, sm.wT, sm.S);
-    __syncthreads();
-    ph_inv2<C>(tid, NT, sm.S, sm.acc);
-    __syncthreads();
+    if (active) grp_inv1<C>(t, job, sm.wT, sm.S);
+    __syncwarp();
+    if (active) grp_inv2<C>(t, job, sm.S, sm.acc);
+    __syncwarp();
 }
 
 // [U] glwe_sample_extraction.rs::extract_lwe_sample_from_glwe_ciphertext(.., MonomialDegree(0)); element e of the LWE
@@ -80,8 +93,8 @@ __device__ __forceinline__ uint64_t sample_extract_elem(const uint64_t* __restri
 // ================================================================================================ PBS (homomorphic_shift_boolean)
 // in: small LWE [nct][n+1]; out: big LWE [nct][kN+1] encrypting bit·2·alpha.
 // [U] wop_pbs.rs::homomorphic_shift_boolean + bootstrap.rs::{blind_rotate_assign, bootstrap}
-template <int N, int K, int L, int B, int NT>
-__global__ void __launch_bounds__(NT, 1)
+template <int N, int K, int L, int B, int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
            const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
     typedef EpCfg<N, K, L, B> C;
@@ -128,6 +141,7 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
         ep_step_device<C, NT>(tid, sm, bsk + ggsw_sz * i,
                               [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, out);
     }
+    __syncthreads();
     constexpr int LW = K * N + 1;
     for (int idx = tid; idx < B * LW; idx += NT) {
         const int b = idx / LW, e = idx - b * LW, ct = ct0 + b;
@@ -180,6 +194,7 @@ vp_kernel(const cplx* __restrict__ ggsw_f, int n_in, int first_ggsw, const uint6
                               [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot); }, base_log, outr);
         deg <<= 1;
     }
+    __syncthreads();
     constexpr int LW = K * N + 1;
     for (int idx = tid; idx < B * LW; idx += NT) {
         const int b = idx / LW, e = idx - b * LW, o = o0 + b;
@@ -227,6 +242,7 @@ cmux_tree_kernel(const cplx* __restrict__ ggsw_f, int n_in, int ggsw_idx, const 
     const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
     const cplx* ggsw = ggsw_f + ((size_t)box * n_in + ggsw_idx) * ggsw_sz;
     ep_step_device<C, NT>(tid, sm, ggsw, [&](int job, int j) { return diff[(size_t)job * N + j]; }, base_log, outr);
+    __syncthreads();
     uint64_t* dst = node_out + (((size_t)box * n_out + o) * n_pairs + pair) * C::G * N;
     for (int idx = tid; idx < C::G * N; idx += NT) dst[idx] = sm.acc[idx];
 }

@@ -3,6 +3,8 @@
 #include "kernels_ep.cuh"
 #include "shape_launch.h"
 
+#include <cstdlib>
+
 namespace tac {
 namespace {
 
@@ -22,19 +24,23 @@ cudaError_t s_poly_fft(const KLaunch& k, const uint64_t* polys, size_t npoly, do
     return cudaGetLastError();
 }
 
-template <int L, int B, int NT>
+template <int L, int B, int NT, int MINB = 1>
 cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
     typedef EpCfg<SN, SK, L, B> C;
     const size_t smem = EpSmem<C>::bytes + 2 * B * sizeof(int);
-    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT>), smem);
-    pbs_kernel<SN, SK, L, B, NT><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT, MINB>), smem);
+    pbs_kernel<SN, SK, L, B, NT, MINB><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
 template <int L>
 cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
 #if TAC_N == 512
     // B ciphertexts per CTA share every BSK load; fewer per CTA when the batch cannot fill the GPU otherwise
-    if (nct >= 4 * k.sm_count) return launch_pbs<L, 4, 320>(k, small, nct, n, bsk, base_log, alpha, out);
+    // Measured on B200 (profiles/): B = 3 with 256 threads (8 warps, 2 per scheduler, 255 registers, no spills) beats B = 4
+    // with 320 threads (10 warps but a 168-register cap per scheduler partition and spills) by 27 %.
+    static const int variant = getenv("TAC_PBS_VARIANT") ? atoi(getenv("TAC_PBS_VARIANT")) : 0;
+    if (nct >= 4 * k.sm_count && variant == 4) return launch_pbs<L, 4, 320>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256>(k, small, nct, n, bsk, base_log, alpha, out);
     if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 160>(k, small, nct, n, bsk, base_log, alpha, out);
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);
 #else
@@ -97,6 +103,7 @@ cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__
         for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
     const int r = rot[blockIdx.x];
     ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int job, int j) { return rot_diff<SN>(sm.acc + (size_t)job * SN, j, r); }, base_log, outr);
+    __syncthreads();
     for (int i = tid; i < C::G * SN; i += NT) g[i] = sm.acc[i];
 }
 template <int L>

@@ -30,7 +30,7 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     // threads before the next pass starts
     auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < C::JOBS) fn(t, job); } };
     groups([&](int t, int job) {
-        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, dig.data(), wT.data(), S.data());
+        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, make_decomp_fast(base_log, L), dig.data(), wT.data(), S.data());
     });
     groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
     for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC>(tid, L, gf.data(), regs[tid].g);
@@ -62,7 +62,7 @@ static void emul_fft(const double* in, double* out_re, double* out_im, int* slot
 
 template <int L> static void digits_t(uint64_t x, int b, double* out) {
     uint32_t w[L];
-    decompose_pair<L>(x, ~x, b, w);
+    decompose_pair<L>(x, ~x, make_decomp_fast(b, L), w);
     for (int s = 0; s < L; s++) { double a, c; unpack_digits(w[s], a, c); out[s] = a; }
 }
 

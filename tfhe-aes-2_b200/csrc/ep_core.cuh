@@ -265,11 +265,44 @@ TAC_HD void decompose_digits(uint64_t x, int b, uint32_t (&dig)[L]) {
         dig[l - 1] = r - (carry << b) + kDigitBias;
     }
 }
+// Fast path: the closed-form balanced decomposition
+//     field_l = ((x + add) >> (64 - b·l)) & (B-1),   digit_l = field_l - B/2          (add = rounding bit + B/2 at every level)
+// agrees with the iterator unless some level is an exact tie (raw digit == B/2  ⇔  field_l == 0, probability ≈ L·2^-b per
+// coefficient); only then the exact routine above is replayed, out of line.
+struct DecompFast {
+    uint64_t add;
+    uint32_t mask, bias_adj;     // bias_adj = kDigitBias - B/2
+    int b;
+};
+TAC_HD DecompFast make_decomp_fast(int b, int l) {
+    DecompFast d;
+    uint64_t add = 1ull << (63 - b * l);
+    for (int lev = 1; lev <= l; lev++) add += (1ull << (b - 1)) << (64 - b * lev);
+    d.add = add; d.mask = (1u << b) - 1u; d.bias_adj = kDigitBias - (1u << (b - 1)); d.b = b;
+    return d;
+}
+#if defined(__CUDACC__)
+template <int L> __device__ __noinline__ void decompose_digits_slow(uint64_t x, int b, uint32_t (&dig)[L]) { decompose_digits<L>(x, b, dig); }
+#else
+template <int L> inline void decompose_digits_slow(uint64_t x, int b, uint32_t (&dig)[L]) { decompose_digits<L>(x, b, dig); }
+#endif
 template <int L>
-TAC_HD void decompose_pair(uint64_t x0, uint64_t x1, int b, uint32_t (&out)[L]) {
+TAC_HD void decompose_digits_fast(uint64_t x, const DecompFast& dc, uint32_t (&dig)[L]) {
+    const uint64_t y = x + dc.add;
+    bool tie = false;
+#pragma unroll
+    for (int l = 1; l <= L; l++) {
+        const uint32_t f = (uint32_t)(y >> (64 - dc.b * l)) & dc.mask;
+        tie = tie || (f == 0u);
+        dig[l - 1] = f + dc.bias_adj;
+    }
+    if (tie) decompose_digits_slow<L>(x, dc.b, dig);
+}
+template <int L>
+TAC_HD void decompose_pair(uint64_t x0, uint64_t x1, const DecompFast& dc, uint32_t (&out)[L]) {
     uint32_t d0[L], d1[L];
-    decompose_digits<L>(x0, b, d0);
-    decompose_digits<L>(x1, b, d1);
+    decompose_digits_fast<L>(x0, dc, d0);
+    decompose_digits_fast<L>(x1, dc, d1);
 #pragma unroll
     for (int s = 0; s < L; s++) out[s] = (d0[s] & 0xFFFFu) | (d1[s] << 16);
 }

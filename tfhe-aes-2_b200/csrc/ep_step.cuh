@@ -48,12 +48,12 @@ struct MacCfg {
 // group phase 1 of a step: decompose the operand polynomial `job` (coef(j) = its coefficient j), keep the digits of
 // levels 1..L-1 in dig, and run forward-FFT pass 1 on the level-L digits straight from registers.
 template <class C, class CoefFn>
-TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, int base_log, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
+TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
                             cplx* __restrict__ S) {
     uint32_t* dj = dig + (size_t)job * (C::L - 1) * C::M;
     fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) {
         uint32_t w[C::L];
-        decompose_pair<C::L>(coef(jj), coef(jj + C::M), base_log, w);
+        decompose_pair<C::L>(coef(jj), coef(jj + C::M), dc, w);
 #pragma unroll
         for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
         unpack_digits(w[C::L - 1], a, b);
@@ -71,7 +71,10 @@ TAC_HD void grp_fwd2(int t, int job, cplx* __restrict__ S) { fft_fwd_pass2<C::N>
 // ggsw: Fourier GGSW of this step, [L][G][G][M] slot-ordered (already scaled by 2^-64 / M).
 // Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that
 // precedes the MAC (the L2 latency hides behind the barrier wait), row p+MAC_DEPTH is requested while row p is multiplied.
-constexpr int MAC_DEPTH = 3;
+#ifndef TAC_MAC_DEPTH
+#define TAC_MAC_DEPTH 5
+#endif
+constexpr int MAC_DEPTH = TAC_MAC_DEPTH;
 template <class C, int NT_MAC>
 TAC_HD void mac_load_row(const cplx* __restrict__ gl, int p, int tau, cplx (&dst)[C::G]) {
 #pragma unroll

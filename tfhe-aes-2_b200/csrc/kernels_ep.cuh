@@ -56,10 +56,11 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     const int job = tid >> 4, t = tid & 15;
     const bool active = job < C::JOBS;
     cplx g[MAC_DEPTH][C::G];            // key prefetch ring (ep_step.cuh)
-    if (active) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, base_log, sm.dig, sm.wT, sm.S);
+    const DecompFast dc = make_decomp_fast(base_log, C::L);
+    if (active) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, dc, sm.dig, sm.wT, sm.S);
+    ph_mac_prefetch<C, MC::NT_MAC>(tid, C::L, ggsw, g);                 // in flight during pass 2 and the barrier
     __syncwarp();
     if (active) grp_fwd2<C>(t, job, sm.S);
-    ph_mac_prefetch<C, MC::NT_MAC>(tid, C::L, ggsw, g);
     __syncthreads();
     ph_mac<C, MC::NT_MAC, MC::SPT>(tid, C::L, ggsw, sm.S, out, g);
     if (C::L == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);         // own slots only: no barrier needed in between
@@ -67,9 +68,9 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
         if (active) grp_fwd1<C>(t, job, lev, sm.dig, sm.wT, sm.S);
+        ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, ggsw, g);
         __syncwarp();
         if (active) grp_fwd2<C>(t, job, sm.S);
-        ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, ggsw, g);
         __syncthreads();
         ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, ggsw, sm.S, out, g);
         if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);

@@ -335,7 +335,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "blocks/s", "h2d_bytes_per_step": int(in_host.numel() * 8 * world),
                     "d2h_bytes_per_step": int(out_host.numel() * 8 * world), "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "pbs_kernel<512,4,3,4,320>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "pbs_kernel<N=512,k=4,l=3,B=3,256 threads>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "peak_source": "DFMA microbenchmark in this run (FP64 is not in MEASURED_PEAKS.json; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                          "algorithmic_flop_per_launch": n_ct_per_launch * FLOP_PER_PBS, "avg_launch_ms": pbs_ms, "launches": int(pbs_launches),

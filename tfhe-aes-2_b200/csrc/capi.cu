@@ -48,6 +48,7 @@ struct tac_ctx {
     uint64_t* pfpksk = nullptr;
     uint64_t* ks_corr = nullptr;
     uint64_t* pfks_corr = nullptr;
+    uint8_t* ks_planes = nullptr;        // byte planes of the KSK
     uint8_t* pfks_planes = nullptr;      // byte planes of the PFPKSK for the tensor-core GEMM (kernels_pfks_tc.cuh)
     uint32_t* pfks_fix = nullptr;        // [0] = count, then uint2 (ct, k) entries
     bool keys_allocated = false, keys_valid = false;
@@ -190,17 +191,22 @@ int stage_event(tac_ctx* ctx, int idx) {
     return TAC_OK;
 }
 
-// keyswitch: in [nct][big+1] → small [nct][n+1]
+constexpr uint32_t kFixCap = 1u << 16;
+// keyswitch on the tensor cores (single digit limb): in [nct][big+1] → small [nct][n+1]
 int stage_ks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* small) {
     const TacParams& p = ctx->p;
-    const int big = ctx->big(), Kd = big * p.ks_l;
-    TRY(ensure(ctx, ctx->ws_ksdig, (size_t)nct * Kd * 4));
-    ks_digits_kernel<<<grid1d((size_t)nct * big, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big, p.ks_b, p.ks_l, ctx->ws_ksdig.as<uint32_t>());
-    TRY(post_launch(ctx, "ks_digits_kernel"));
-    return gemm(ctx, ctx->ws_ksdig.as<uint32_t>(), nct, Kd, ctx->ksk, p.n + 1, 1, ctx->ks_corr, in + big, (size_t)big + 1, small);
+    const int big = ctx->big(), Kd = big * p.ks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
+    const int W = p.n + 1, mpad = ((nct + TC_MT - 1) / TC_MT) * TC_MT;
+    TRY(ensure(ctx, ctx->ws_ksdig, (size_t)nkb * 2 * mpad * 16));
+    uint8_t* DA = ctx->ws_ksdig.as<uint8_t>();
+    pfks_digits_tc_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+        in, nct, mpad, big + 1, p.ks_b, p.ks_l, Kd, nkb, 1, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), 0);
+    TRY(post_launch(ctx, "ks_digits_tc_kernel"));
+    dim3 grid((W + TC_NT - 1) / TC_NT, mpad / TC_MT);
+    lwe_gemm_tc_kernel<1><<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->ks_planes, W, 1, nkb, ctx->ks_corr, in + big, (size_t)big + 1, small);
+    return post_launch(ctx, "lwe_gemm_tc_kernel<1>");
 }
 // PFKS with all k+1 keys on the tensor cores: in [nct][big+1] → ggsw_std [nct][G][G·N]
-constexpr uint32_t kFixCap = 1u << 16;
 int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     const TacParams& p = ctx->p;
     const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
@@ -215,11 +221,11 @@ int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     CU(cudaMemsetAsync(ctx->pfks_fix, 0, 4, ctx->stream));
     uint8_t* DA = ctx->ws_pfdig.as<uint8_t>();
     pfks_digits_tc_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-        in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), kFixCap);
+        in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, 0, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), kFixCap);
     TRY(post_launch(ctx, "pfks_digits_tc_kernel"));
     dim3 grid(ctx->G() * (W / TC_NT), mpad / TC_MT);
-    pfks_gemm_tc_kernel<<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, ggsw);
-    TRY(post_launch(ctx, "pfks_gemm_tc_kernel"));
+    lwe_gemm_tc_kernel<2><<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, nullptr, 0, ggsw);
+    TRY(post_launch(ctx, "lwe_gemm_tc_kernel<2>"));
     pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), kFixCap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
     return post_launch(ctx, "pfks_fixup_kernel");
 }
@@ -343,7 +349,7 @@ void tac_ctx_destroy(tac_ctx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->pfks_planes, (void*)ctx->pfks_fix, (void*)ctx->wT,
+    for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->pfks_planes, (void*)ctx->ks_planes, (void*)ctx->pfks_fix, (void*)ctx->wT,
                     (void*)ctx->key_sched})
         if (p) cudaFree(p);
     for (auto& l : ctx->luts) cudaFree(l.dev);
@@ -416,6 +422,8 @@ int tac_ctx_alloc_keys(tac_ctx* ctx) {
         const int Kd = (ctx->big() + 1) * ctx->p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
         CU(cudaMalloc(&ctx->pfks_planes, (size_t)ctx->G() * nkb * TC_KB * ctx->G() * ctx->p.N * 8));
         CU(cudaMalloc(&ctx->pfks_fix, 8 + (size_t)kFixCap * 8));
+        const int Kd_ks = ctx->big() * ctx->p.ks_l, nkb_ks = (Kd_ks + TC_KB - 1) / TC_KB, tiles_ks = (ctx->p.n + 1 + TC_NT - 1) / TC_NT;
+        CU(cudaMalloc(&ctx->ks_planes, (size_t)nkb_ks * tiles_ks * 8 * 2 * TC_NT * 16));
     }
     ctx->keys_allocated = true;
     return TAC_OK;
@@ -456,6 +464,10 @@ int tac_ctx_keys_ready(tac_ctx* ctx) {
         const size_t units = (size_t)ctx->G() * nkb * (W / TC_NT) * 2 * TC_NT;
         pfks_key_planes_kernel<<<grid1d(units, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfpksk, ctx->G(), Kd_pf, (int)W, nkb, ctx->pfks_planes);
         TRY(post_launch(ctx, "pfks_key_planes_kernel"));
+        const int nkb_ks = (Kd_ks + TC_KB - 1) / TC_KB, tiles_ks = (p.n + 1 + TC_NT - 1) / TC_NT;
+        const size_t units_ks = (size_t)nkb_ks * tiles_ks * 2 * TC_NT;
+        pfks_key_planes_kernel<<<grid1d(units_ks, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->ksk, 1, Kd_ks, p.n + 1, nkb_ks, ctx->ks_planes);
+        TRY(post_launch(ctx, "ks_key_planes_kernel"));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     ctx->keys_valid = true;

@@ -1,4 +1,4 @@
-// kernels_pfks_tc.cuh — private functional packing keyswitch on the tensor cores.
+// kernels_pfks_tc.cuh — the two keyswitches (LWE keyswitch, private functional packing keyswitch) on the tensor cores.
 //
 // out[ct][j][col] = corr[j][col] − Σ_k d'[ct][k]·key[j][k][col]  (mod 2^64) is an exact integer GEMM with M = ciphertexts,
 // K = (kN+1)·l digits, N = (k+1)·(k+1)N columns.  It is mapped to unsigned 8-bit tensor-core MMAs by splitting both operands
@@ -6,6 +6,7 @@
 //                    key = Σ_{b<8} 2^(8b)·key_b.
 // Only limb pairs of weight 8(a+b) < 64 matter mod 2^64: (a0,b) for b = 0..7 and (a1,b) for b = 0..6 — 15 MMAs per tile and
 // k-block, accumulated by weight into 8 int32 tiles (each sum stays below 2·4128·255² < 2^31) and recombined at the end.
+// The LWE keyswitch (digits d' ∈ [0, 2^3]) is the same GEMM with a single digit limb (NLIMB = 1, 8 MMAs).
 //
 // Layouts (one 32-wide k-block at a time, every fragment read is a conflict-free 32-bit shared-memory load):
 //   digit planes  DA[limb 2][kb][khalf 2][ct (padded to 128)][16 B]
@@ -26,7 +27,9 @@ constexpr int TC_STAGES = 3;
 // ---- digits: exact PFKS decomposition (closest_representable + iterator), biased by B/2, split into two byte planes.
 // One thread produces 16 consecutive k of one ciphertext.  d' == 2^16 (digit = +B/2, only on exact ties) is stored as 0 and
 // recorded in the fix-up list.
-__global__ void pfks_digits_tc_kernel(const uint64_t* __restrict__ in, int nct, int mpad, int big1, int b, int l, int Kd, int nkb,
+// ks_mode = 0: PFKS (closest_representable first; storage index s ↔ level s+1).
+// ks_mode = 1: LWE keyswitch (mask elements only, in_stride words per ciphertext; storage index s ↔ level l-s; one limb).
+__global__ void pfks_digits_tc_kernel(const uint64_t* __restrict__ in, int nct, int mpad, int in_stride, int b, int l, int Kd, int nkb, int ks_mode,
                                       uint8_t* __restrict__ DA, uint32_t* __restrict__ fix_count, uint2* __restrict__ fix_list, uint32_t fix_cap) {
     const size_t total = (size_t)mpad * nkb * 2;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
@@ -39,8 +42,9 @@ __global__ void pfks_digits_tc_kernel(const uint64_t* __restrict__ in, int nct, 
             for (int kq = 0; kq < 16; kq++) {
                 const int k = kb * TC_KB + khalf * 16 + kq;
                 if (k >= Kd) continue;
-                const int i = k / l, lev = k - i * l + 1;
-                uint64_t st = decomp_init_state(closest_representable(in[(size_t)ct * big1 + i], b, l), b, l);
+                const int i = k / l, lev = ks_mode ? l - (k - i * l) : k - i * l + 1;
+                const uint64_t x = in[(size_t)ct * in_stride + i];
+                uint64_t st = decomp_init_state(ks_mode ? x : closest_representable(x, b, l), b, l);
                 int64_t d = 0;
                 for (int q2 = l; q2 >= lev; q2--) d = decomp_next(st, b);
                 uint32_t dp = (uint32_t)(d + (int64_t)(1u << (b - 1)));
@@ -56,13 +60,13 @@ __global__ void pfks_digits_tc_kernel(const uint64_t* __restrict__ in, int nct, 
         const size_t plane = (size_t)nkb * 2 * mpad * 16;
         const size_t off = (((size_t)kb * 2 + khalf) * mpad + ct) * 16;
         *reinterpret_cast<uint4*>(DA + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-        *reinterpret_cast<uint4*>(DA + plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        if (!ks_mode) *reinterpret_cast<uint4*>(DA + plane + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     }
 }
 
 // ---- key planes (once per key upload)
 __global__ void pfks_key_planes_kernel(const uint64_t* __restrict__ key, int nkeys, int Kd, int W, int nkb, uint8_t* __restrict__ KP) {
-    const int ntiles = W / TC_NT;
+    const int ntiles = (W + TC_NT - 1) / TC_NT;
     const size_t total = (size_t)nkeys * nkb * ntiles * 2 * TC_NT;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
         const int n = (int)(idx % TC_NT);
@@ -77,7 +81,7 @@ __global__ void pfks_key_planes_kernel(const uint64_t* __restrict__ key, int nke
 #pragma unroll
         for (int kq = 0; kq < 16; kq++) {
             const int k = kb * TC_KB + khalf * 16 + kq;
-            const uint64_t v = (k < Kd) ? key[((size_t)j * Kd + k) * W + tile * TC_NT + n] : 0ull;
+            const uint64_t v = (k < Kd && tile * TC_NT + n < W) ? key[((size_t)j * Kd + k) * W + tile * TC_NT + n] : 0ull;
 #pragma unroll
             for (int bb = 0; bb < 8; bb++) pl[bb][kq >> 2] |= (uint32_t)((v >> (8 * bb)) & 0xFFull) << (8 * (kq & 3));
         }
@@ -100,13 +104,15 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// ---- the GEMM: CTA = 128 ciphertexts × 32 columns, 8 warps as 4 (M) × 2 (N), warp tile 32 × 16
+// ---- the GEMM: CTA = 128 ciphertexts × 32 columns, 8 warps as 4 (M) × 2 (N), warp tile 32 × 16.  NLIMB digit limbs.
+// out[ct][j][col] = corr[j][col] − Σ (+ last_col_add[ct·add_stride] on the last column: the LWE body of the keyswitch)
+template <int NLIMB>
 __global__ void __launch_bounds__(256, 1)
-pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uint8_t* __restrict__ KP, int W, int nkeys, int nkb,
-                    const uint64_t* __restrict__ corr, uint64_t* __restrict__ out) {
-    __shared__ __align__(16) uint32_t As[TC_STAGES][2 * 2 * TC_MT * 4];     // [limb][khalf][row][4 words]
+lwe_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uint8_t* __restrict__ KP, int W, int nkeys, int nkb,
+                   const uint64_t* __restrict__ corr, const uint64_t* __restrict__ last_col_add, size_t add_stride, uint64_t* __restrict__ out) {
+    __shared__ __align__(16) uint32_t As[TC_STAGES][NLIMB * 2 * TC_MT * 4]; // [limb][khalf][row][4 words]
     __shared__ __align__(16) uint32_t Bs[TC_STAGES][8 * 2 * TC_NT * 4];     // [byte][khalf][n][4 words]
-    const int ntiles = W / TC_NT;
+    const int ntiles = (W + TC_NT - 1) / TC_NT;
     const int j = blockIdx.x / ntiles, tile = blockIdx.x - j * ntiles;
     const int ct0 = blockIdx.y * TC_MT;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -118,8 +124,8 @@ pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uin
     auto load_stage = [&](int stage, int kb) {
         // A: 4 chunks of 2 KB ([limb][khalf] × 128 rows × 16 B); B: one 8 KB chunk.  256 threads × 4 × 16 B.
 #pragma unroll
-        for (int r = 0; r < 2; r++) {
-            const int e = tid + r * 256;                 // 0..511: 16-byte unit of the A stage
+        for (int r = 0; r < NLIMB; r++) {
+            const int e = tid + r * 256;                 // 16-byte unit of the A stage
             const int chunk = e >> 7, row = e & 127;     // chunk = limb*2 + khalf
             const uint8_t* src = DA + (size_t)(chunk >> 1) * a_plane + (((size_t)kb * 2 + (chunk & 1)) * mpad + ct0 + row) * 16;
             cp_async16(&As[stage][e * 4], src);
@@ -156,9 +162,9 @@ pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uin
         }
         const uint32_t* as = As[kb % TC_STAGES];
         const uint32_t* bs = Bs[kb % TC_STAGES];
-        uint32_t a[2][2][4];                             // [limb][mi][frag]
+        uint32_t a[NLIMB][2][4];                         // [limb][mi][frag]
 #pragma unroll
-        for (int limb = 0; limb < 2; limb++)
+        for (int limb = 0; limb < NLIMB; limb++)
 #pragma unroll
             for (int mi = 0; mi < 2; mi++) {
                 const int row = wm * 32 + mi * 16 + g;
@@ -177,7 +183,7 @@ pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uin
 #pragma unroll
                 for (int mi = 0; mi < 2; mi++) {
                     mma_u8(acc[mi][ni][bb], a[0][mi], b0, b1);
-                    if (bb < 7) mma_u8(acc[mi][ni][bb + 1], a[1][mi], b0, b1);
+                    if (NLIMB > 1 && bb < 7) mma_u8(acc[mi][ni][bb + 1], a[NLIMB - 1][mi], b0, b1);
                 }
             }
         }
@@ -189,6 +195,7 @@ pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uin
 #pragma unroll
         for (int ni = 0; ni < 2; ni++) {
             const int col = tile * TC_NT + wn * 16 + ni * 8 + 2 * t;
+            if (col >= W) continue;                      // W is even: col + 1 < W as well
             const uint64_t c0 = corr[(size_t)j * W + col], c1 = corr[(size_t)j * W + col + 1];
 #pragma unroll
             for (int h = 0; h < 2; h++) {
@@ -200,7 +207,9 @@ pfks_gemm_tc_kernel(const uint8_t* __restrict__ DA, int nct, int mpad, const uin
                     s0 += (uint64_t)(uint32_t)acc[mi][ni][w][2 * h] << (8 * w);
                     s1 += (uint64_t)(uint32_t)acc[mi][ni][w][2 * h + 1] << (8 * w);
                 }
-                *reinterpret_cast<ulonglong2*>(out + ((size_t)ct * nkeys + j) * W + col) = make_ulonglong2(c0 - s0, c1 - s1);
+                uint64_t v0 = c0 - s0, v1 = c1 - s1;
+                if (last_col_add && col + 1 == W - 1) v1 += last_col_add[(size_t)ct * add_stride];
+                *reinterpret_cast<ulonglong2*>(out + ((size_t)ct * nkeys + j) * W + col) = make_ulonglong2(v0, v1);
             }
         }
 }

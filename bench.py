@@ -206,6 +206,7 @@ def run_gpu(args):
     device = torch.device("cuda", local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout for the one JSON line
         dist.init_process_group("nccl", device_id=device)
     tac = importlib.import_module("tfhe-aes-2_b200")
     dmod = importlib.import_module("tfhe-aes-2_b200.distributed")

@@ -7,6 +7,7 @@
 #include <vector>
 
 using namespace tac;
+constexpr int MAC_DEPTH = 5;      // ring depth the shipped PBS kernels use
 
 template <int N, int K, int L, int B, int NT>
 static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
@@ -15,31 +16,32 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     std::vector<cplx> wT(C::M); build_wT(N, wT.data());
     // Fourier GGSW with the kernels' own key transform
     const int polys = L * C::G * C::G;
-    std::vector<cplx> gf((size_t)polys * C::M), buf(C::M);
+    std::vector<cplx> gf((size_t)polys * C::M), kbuf(C::M);
     for (int q = 0; q < polys; q++) {
-        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, wT.data(), buf.data());
-        for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, buf.data());
-        for (int s = 0; s < C::M; s++) gf[(size_t)q * C::M + s] = buf[s];
+        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, wT.data(), kbuf.data());
+        for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, kbuf.data());
+        for (int s = 0; s < C::M; s++) gf[(size_t)q * C::M + s] = kbuf[s];
     }
     struct Regs { cplx v[MC::SPT][C::B][C::G]; cplx g[MAC_DEPTH][C::G]; };
     std::vector<Regs> regs(NT);
     for (auto& r : regs) for (int a = 0; a < MC::SPT; a++) for (int b = 0; b < C::B; b++) for (int c = 0; c < C::G; c++) r.v[a][b][c] = mk(0, 0);
     std::vector<cplx> S(C::s_cplx);
     std::vector<uint32_t> dig(C::dig_words + 1);
+    const DecompFast dc = make_decomp_fast(base_log, L);
     // phase order of ep_step_device (kernels_ep.cuh); a group-local __syncwarp() is modelled by finishing a pass for all
     // threads before the next pass starts
     auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < C::JOBS) fn(t, job); } };
     groups([&](int t, int job) {
-        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, make_decomp_fast(base_log, L), dig.data(), wT.data(), S.data());
+        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, dc, dig.data(), wT.data(), S.data());
     });
     groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
-    for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC>(tid, L, gf.data(), regs[tid].g);
-    for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, L, gf.data(), S.data(), regs[tid].v, regs[tid].g);
+    for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, L, gf.data(), regs[tid].g);
+    for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, L, gf.data(), S.data(), regs[tid].v, regs[tid].g);
     for (int lev = L - 1; lev >= 1; lev--) {
-        groups([&](int t, int job) { grp_fwd1<C>(t, job, lev, dig.data(), wT.data(), S.data()); });
+        groups([&](int t, int job) { grp_fwd1<C>(t, job, lev, dc, dig.data(), wT.data(), S.data()); });
         groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
-        for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, gf.data(), regs[tid].g);
-        for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, gf.data(), S.data(), regs[tid].v, regs[tid].g);
+        for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, gf.data(), regs[tid].g);
+        for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, gf.data(), S.data(), regs[tid].v, regs[tid].g);
     }
     for (int tid = 0; tid < NT; tid++) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, S.data(), regs[tid].v);
     groups([&](int t, int job) { grp_inv1<C>(t, job, wT.data(), S.data()); });
@@ -62,8 +64,9 @@ static void emul_fft(const double* in, double* out_re, double* out_im, int* slot
 
 template <int L> static void digits_t(uint64_t x, int b, double* out) {
     uint32_t w[L];
-    decompose_pair<L>(x, ~x, make_decomp_fast(b, L), w);
-    for (int s = 0; s < L; s++) { double a, c; unpack_digits(w[s], a, c); out[s] = a; }
+    const DecompFast dc = make_decomp_fast(b, L);
+    decompose_pair<L>(x, ~x, dc, w);
+    for (int s = 0; s < L; s++) { double a, c; unpack_digits(w[s], dc, a, c); out[s] = a; }
 }
 
 extern "C" {

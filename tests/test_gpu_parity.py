@@ -121,7 +121,15 @@ def test_vertical_packing_from_oracle_ggsws(gpu64, oracle64, ol):
         assert ck.decrypt_bytes(got[i]) == f(v).to_bytes(3, "big") == oracle64.decrypt_bytes(ref)
         want = ck.decrypt_bits(ref).astype(np.uint64) << np.uint64(63)
         e_gpu, e_ref = signed(ck.decrypt_phases(got[i]) - want), signed(ck.decrypt_phases(ref) - want)
-        assert np.abs(e_gpu).max() < 2.0**59 and np.abs(e_gpu - e_ref).max() < 2.0**50
+        assert np.abs(e_gpu).max() < 2.0**59
+        # Same computation up to f64 rounding (|Δ| ≈ 2^35) — except where a CMux operand coefficient sits within that
+        # rounding error of a decomposition boundary ((k+½)·2^51 for l = 1, B = 2^13; ≈ 2^-16 per coefficient): the two
+        # runs then pick neighbouring digits, both closest-representable, and the phases differ by one unit 2^51 times
+        # a secret-key bit.  Allow that, and nothing else: Δ = k·2^51 + δ with |k| <= 2 on a few outputs, |δ| < 2^40.
+        d = e_gpu - e_ref
+        k = np.rint(d / 2.0**51)
+        assert np.abs(d - k * 2.0**51).max() < 2.0**40
+        assert np.abs(k).max() <= 2 and np.count_nonzero(k) <= 6, k.tolist()
 
 
 # ---------------------------------------------------------------------------------------------- the operator, decrypt-checked

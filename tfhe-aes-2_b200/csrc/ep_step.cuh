@@ -4,7 +4,7 @@
 //   acc   uint64  [B][G][N]       the B accumulators (G = k+1 polynomials each)
 //   S     cplx    [B*G][M]        one FFT buffer per (ciphertext, polynomial); reused for the MAC output
 //   dig   uint32  [B*G][L-1][M]   decomposition digits of levels 1..L-1 of this step (level L is consumed at once),
-//                                 samples (jj, jj+M) packed as biased u16 pairs
+//                                 samples (jj, jj+M) packed as 16-bit fields digit + B/2
 //   wT    cplx    [M]             combined twist/twiddle table (ep_core.cuh)
 // Per-thread registers that live across the phases of one step: out[SPT][B][G] (Fourier-domain accumulators of the
 // frequency slots this thread owns).
@@ -25,8 +25,28 @@
 
 namespace tac {
 
+// Key loads: read-only path; TAC_LDG_MODE picks the cache hint (0: ld.global.nc, 1: + L1::no_allocate, 2: + L1::evict_first,
+// 3: ld.global.cg-style L2-only via .L1::no_allocate.L2::128B prefetch size) — measured with tools/pbs_bench.cu.
+#ifndef TAC_LDG_MODE
+#define TAC_LDG_MODE 0
+#endif
 #if defined(__CUDA_ARCH__)
-#define TAC_LDG(p) __ldg(p)
+__device__ __forceinline__ cplx tac_ldg_key(const cplx* p) {
+    cplx r;
+#if TAC_LDG_MODE == 1
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#elif TAC_LDG_MODE == 2
+    asm volatile("ld.global.nc.L1::evict_first.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#elif TAC_LDG_MODE == 3
+    asm volatile("ld.global.nc.L1::no_allocate.L2::128B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#elif TAC_LDG_MODE == 4
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+#else
+    r = __ldg(p);
+#endif
+    return r;
+}
+#define TAC_LDG(p) tac_ldg_key(p)
 #else
 #define TAC_LDG(p) (*(p))
 #endif
@@ -56,14 +76,14 @@ TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, u
         decompose_pair<C::L>(coef(jj), coef(jj + C::M), dc, w);
 #pragma unroll
         for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
-        unpack_digits(w[C::L - 1], a, b);
+        unpack_digits(w[C::L - 1], dc, a, b);
     }, wT, S + (size_t)job * C::M);
 }
 // forward FFT pass 1 of the cached level-`lev` digits (lev < L)
 template <class C>
-TAC_HD void grp_fwd1(int t, int job, int lev, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+TAC_HD void grp_fwd1(int t, int job, int lev, const DecompFast& dc, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     const uint32_t* d = dig + ((size_t)job * (C::L - 1) + (lev - 1)) * C::M;
-    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], a, b); }, wT, S + (size_t)job * C::M);
+    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, wT, S + (size_t)job * C::M);
 }
 template <class C>
 TAC_HD void grp_fwd2(int t, int job, cplx* __restrict__ S) { fft_fwd_pass2<C::N>(t, S + (size_t)job * C::M); }
@@ -71,23 +91,20 @@ TAC_HD void grp_fwd2(int t, int job, cplx* __restrict__ S) { fft_fwd_pass2<C::N>
 // ggsw: Fourier GGSW of this step, [L][G][G][M] slot-ordered (already scaled by 2^-64 / M).
 // Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that
 // precedes the MAC (the L2 latency hides behind the barrier wait), row p+MAC_DEPTH is requested while row p is multiplied.
-#ifndef TAC_MAC_DEPTH
-#define TAC_MAC_DEPTH 5
-#endif
-constexpr int MAC_DEPTH = TAC_MAC_DEPTH;
+// MAC_DEPTH is a kernel template parameter (register budget: each ring entry is G complex values).
 template <class C, int NT_MAC>
 TAC_HD void mac_load_row(const cplx* __restrict__ gl, int p, int tau, cplx (&dst)[C::G]) {
 #pragma unroll
     for (int c = 0; c < C::G; c++) dst[c] = TAC_LDG(gl + (size_t)(p * C::G + c) * C::M + tau);
 }
-template <class C, int NT_MAC>
+template <class C, int NT_MAC, int MAC_DEPTH>
 TAC_HD void ph_mac_prefetch(int tid, int lev, const cplx* __restrict__ ggsw, cplx (&g)[MAC_DEPTH][C::G]) {
     if (tid >= NT_MAC) return;
     const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
 #pragma unroll
     for (int p = 0; p < MAC_DEPTH && p < C::G; p++) mac_load_row<C, NT_MAC>(gl, p, tid, g[p]);
 }
-template <class C, int NT_MAC, int SPT>
+template <class C, int NT_MAC, int SPT, int MAC_DEPTH>
 TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G],
                    cplx (&g)[MAC_DEPTH][C::G]) {
     if (tid >= NT_MAC) return;

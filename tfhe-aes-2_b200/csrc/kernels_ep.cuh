@@ -48,37 +48,56 @@ struct EpSmem {
 // one step on the operand coef(job, j); the accumulators receive  acc += GGSW ⊡ operand.
 // Ends with a __syncwarp(): the accumulator rows of a job are only touched by the job's own 16-thread group, so the next
 // step's decomposition may follow without a CTA barrier.  (Readers of acc from other groups must __syncthreads() first.)
-template <class C, int NT, class CoefFn>
+// TAC_EP_DBG (development only, tools/pbs_bench.cu): bit 0 skips the Fourier MAC, bit 1 the forward FFT passes, bit 2 the
+// inverse passes, bit 3 the decomposition — timing attribution of the phases in situ; the results are then meaningless.
+#ifndef TAC_EP_DBG
+#define TAC_EP_DBG 0
+#endif
+template <class C, int NT, int MAC_DEPTH = 5, class CoefFn>
 __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, const cplx* __restrict__ ggsw, CoefFn coef, int base_log,
                                                cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G]) {
     typedef MacCfg<C, NT> MC;
     static_assert(NT / 16 >= C::JOBS, "one 16-thread group per operand polynomial");
+    constexpr bool DO_MAC = !(TAC_EP_DBG & 1), DO_FWD = !(TAC_EP_DBG & 2), DO_INV = !(TAC_EP_DBG & 4), DO_DEC = !(TAC_EP_DBG & 8);
     const int job = tid >> 4, t = tid & 15;
     const bool active = job < C::JOBS;
     cplx g[MAC_DEPTH][C::G];            // key prefetch ring (ep_step.cuh)
     const DecompFast dc = make_decomp_fast(base_log, C::L);
-    if (active) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, dc, sm.dig, sm.wT, sm.S);
-    ph_mac_prefetch<C, MC::NT_MAC>(tid, C::L, ggsw, g);                 // in flight during pass 2 and the barrier
+    // (A variant that ping-pongs between two FFT buffers, so that mac(l) and the transforms of level l-1 share one barrier
+    // interval — L+1 barriers instead of 2L — measured 3 % SLOWER on B200 (tools/pbs_bench.cu, 123.2 vs 119.4 ms for 6144
+    // ciphertexts) and costs 61 KB more shared memory; the single-buffer schedule below is the one that ships.)
+    if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, dc, sm.dig, sm.wT, sm.S);
+    if (active && !DO_FWD && DO_DEC) {          // decomposition alone
+        for (int m = 0; m < C::M / 16; m++) {
+            uint32_t w[C::L];
+            decompose_pair<C::L>(coef(job, t + 16 * m), coef(job, t + 16 * m + C::M), dc, w);
+#pragma unroll
+            for (int s2 = 0; s2 + 1 < C::L; s2++) sm.dig[((size_t)job * (C::L - 1) + s2) * C::M + t + 16 * m] = w[s2];
+            sm.S[(size_t)job * C::M + t + 16 * m].x = (double)w[C::L - 1];
+        }
+    }
+    if (active && DO_FWD && !DO_DEC) grp_fwd1<C>(t, job, 1, dc, sm.dig, sm.wT, sm.S);
+    if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);                 // in flight during pass 2 and the barrier
     __syncwarp();
-    if (active) grp_fwd2<C>(t, job, sm.S);
+    if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
     __syncthreads();
-    ph_mac<C, MC::NT_MAC, MC::SPT>(tid, C::L, ggsw, sm.S, out, g);
+    if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, C::L, ggsw, sm.S, out, g);
     if (C::L == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);         // own slots only: no barrier needed in between
     __syncthreads();
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
-        if (active) grp_fwd1<C>(t, job, lev, sm.dig, sm.wT, sm.S);
-        ph_mac_prefetch<C, MC::NT_MAC>(tid, lev, ggsw, g);
+        if (active && DO_FWD) grp_fwd1<C>(t, job, lev, dc, sm.dig, sm.wT, sm.S);
+        if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
         __syncwarp();
-        if (active) grp_fwd2<C>(t, job, sm.S);
+        if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
         __syncthreads();
-        ph_mac<C, MC::NT_MAC, MC::SPT>(tid, lev, ggsw, sm.S, out, g);
+        if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, ggsw, sm.S, out, g);
         if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);
         __syncthreads();
     }
-    if (active) grp_inv1<C>(t, job, sm.wT, sm.S);
+    if (active && DO_INV) grp_inv1<C>(t, job, sm.wT, sm.S);
     __syncwarp();
-    if (active) grp_inv2<C>(t, job, sm.S, sm.acc);
+    if (active && DO_INV) grp_inv2<C>(t, job, sm.S, sm.acc);
     __syncwarp();
 }
 
@@ -94,7 +113,7 @@ __device__ __forceinline__ uint64_t sample_extract_elem(const uint64_t* __restri
 // ================================================================================================ PBS (homomorphic_shift_boolean)
 // in: small LWE [nct][n+1]; out: big LWE [nct][kN+1] encrypting bit·2·alpha.
 // [U] wop_pbs.rs::homomorphic_shift_boolean + bootstrap.rs::{blind_rotate_assign, bootstrap}
-template <int N, int K, int L, int B, int NT, int MINB>
+template <int N, int K, int L, int B, int NT, int MINB, int MAC_DEPTH = 5>
 __global__ void __launch_bounds__(NT, MINB)
 pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
            const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
@@ -139,7 +158,7 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
     for (int i = 0; i < n; i++) {
         const int* rot = rot_sm + (i & 1) * B;
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
-        ep_step_device<C, NT>(tid, sm, bsk + ggsw_sz * i,
+        ep_step_device<C, NT, MAC_DEPTH>(tid, sm, bsk + ggsw_sz * i,
                               [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, out);
     }
     __syncthreads();

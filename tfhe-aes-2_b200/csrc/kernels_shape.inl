@@ -24,12 +24,12 @@ cudaError_t s_poly_fft(const KLaunch& k, const uint64_t* polys, size_t npoly, do
     return cudaGetLastError();
 }
 
-template <int L, int B, int NT, int MINB = 1>
+template <int L, int B, int NT, int MINB = 1, int DEPTH = 5>
 cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
     typedef EpCfg<SN, SK, L, B> C;
     const size_t smem = EpSmem<C>::bytes + 2 * B * sizeof(int);
-    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT, MINB>), smem);
-    pbs_kernel<SN, SK, L, B, NT, MINB><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH>), smem);
+    pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
 template <int L>
@@ -40,8 +40,8 @@ cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, 
     // with 320 threads (10 warps but a 168-register cap per scheduler partition and spills) by 27 %.
     static const int variant = getenv("TAC_PBS_VARIANT") ? atoi(getenv("TAC_PBS_VARIANT")) : 0;
     if (nct >= 4 * k.sm_count && variant == 4) return launch_pbs<L, 4, 320>(k, small, nct, n, bsk, base_log, alpha, out);
-    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256>(k, small, nct, n, bsk, base_log, alpha, out);
-    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 160>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 160, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation

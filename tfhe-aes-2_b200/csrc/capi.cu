@@ -3,7 +3,7 @@
 // no usable CUDA device.
 #include "../../include/tfhe_aes_cuda.h"
 #include "kernels_common.cuh"
-#include "kernels_pfks_tc.cuh"
+#include "kernels_gemm_umma.cuh"
 #include "ep_step.cuh"
 #include "shape_launch.h"
 
@@ -49,7 +49,7 @@ struct tac_ctx {
     uint64_t* ks_corr = nullptr;
     uint64_t* pfks_corr = nullptr;
     uint8_t* ks_planes = nullptr;        // byte planes of the KSK
-    uint8_t* pfks_planes = nullptr;      // byte planes of the PFPKSK for the tensor-core GEMM (kernels_pfks_tc.cuh)
+    uint8_t* pfks_planes = nullptr;      // byte-plane tiles of the PFPKSK for the tcgen05 GEMM (kernels_gemm_umma.cuh)
     uint32_t* pfks_fix = nullptr;        // [0] = count, then uint2 (ct, k) entries
     bool keys_allocated = false, keys_valid = false;
     // tables
@@ -192,25 +192,33 @@ int stage_event(tac_ctx* ctx, int idx) {
 }
 
 constexpr uint32_t kFixCap = 1u << 16;
+// exact integer GEMM on the 5th-generation tensor cores (kernels_gemm_umma.cuh); DA / KP are operand tiles
+template <int NLIMB>
+int gemm_umma(tac_ctx* ctx, const uint8_t* DA, int nct, const uint8_t* KP, int W, int nkeys, int nkb, const uint64_t* corr,
+              const uint64_t* last_col_add, size_t add_stride, uint64_t* out) {
+    CU(cudaFuncSetAttribute(lwe_gemm_umma_kernel<NLIMB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UgCfg<NLIMB>::SMEM));
+    const int mtiles = (nct + UG_MT - 1) / UG_MT, ntiles = (W + UG_NT - 1) / UG_NT;
+    lwe_gemm_umma_kernel<NLIMB><<<mtiles * ntiles * nkeys, UG_THREADS, UgCfg<NLIMB>::SMEM, ctx->stream>>>(DA, nct, mtiles, KP, W, nkeys, nkb, corr, last_col_add,
+                                                                                                      add_stride, out);
+    return post_launch(ctx, NLIMB == 2 ? "lwe_gemm_umma_kernel<2>" : "lwe_gemm_umma_kernel<1>");
+}
 // keyswitch on the tensor cores (single digit limb): in [nct][big+1] → small [nct][n+1]
 int stage_ks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* small) {
     const TacParams& p = ctx->p;
-    const int big = ctx->big(), Kd = big * p.ks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
-    const int W = p.n + 1, mpad = ((nct + TC_MT - 1) / TC_MT) * TC_MT;
+    const int big = ctx->big(), Kd = big * p.ks_l, nkb = (Kd + UG_KB - 1) / UG_KB;
+    const int W = p.n + 1, mpad = ((nct + UG_MT - 1) / UG_MT) * UG_MT;
     TRY(ensure(ctx, ctx->ws_ksdig, (size_t)nkb * 2 * mpad * 16));
     uint8_t* DA = ctx->ws_ksdig.as<uint8_t>();
-    pfks_digits_tc_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+    umma_digit_tiles_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
         in, nct, mpad, big + 1, p.ks_b, p.ks_l, Kd, nkb, 1, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), 0);
-    TRY(post_launch(ctx, "ks_digits_tc_kernel"));
-    dim3 grid((W + TC_NT - 1) / TC_NT, mpad / TC_MT);
-    lwe_gemm_tc_kernel<1><<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->ks_planes, W, 1, nkb, ctx->ks_corr, in + big, (size_t)big + 1, small);
-    return post_launch(ctx, "lwe_gemm_tc_kernel<1>");
+    TRY(post_launch(ctx, "umma_digit_tiles_kernel(ks)"));
+    return gemm_umma<1>(ctx, DA, nct, ctx->ks_planes, W, 1, nkb, ctx->ks_corr, in + big, (size_t)big + 1, small);
 }
 // PFKS with all k+1 keys on the tensor cores: in [nct][big+1] → ggsw_std [nct][G][G·N]
 int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     const TacParams& p = ctx->p;
-    const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
-    const int W = ctx->G() * p.N, mpad = ((nct + TC_MT - 1) / TC_MT) * TC_MT;
+    const int big1 = ctx->big() + 1, Kd = big1 * p.pfks_l, nkb = (Kd + UG_KB - 1) / UG_KB;
+    const int W = ctx->G() * p.N, mpad = ((nct + UG_MT - 1) / UG_MT) * UG_MT;
     if (p.pfks_b > 16) {       // digits wider than 16 bits (params_sqrd_lvl_1: base 2^24): 64-bit integer-pipe GEMM
         TRY(ensure(ctx, ctx->ws_pfdig, (size_t)nct * Kd * 4));
         pfks_digits_kernel<<<grid1d((size_t)nct * big1, 256, ctx->sm_count), 256, 0, ctx->stream>>>(in, nct, big1, p.pfks_b, p.pfks_l, ctx->ws_pfdig.as<uint32_t>());
@@ -220,12 +228,10 @@ int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     TRY(ensure(ctx, ctx->ws_pfdig, (size_t)2 * nkb * 2 * mpad * 16));
     CU(cudaMemsetAsync(ctx->pfks_fix, 0, 4, ctx->stream));
     uint8_t* DA = ctx->ws_pfdig.as<uint8_t>();
-    pfks_digits_tc_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+    umma_digit_tiles_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
         in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, 0, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), kFixCap);
-    TRY(post_launch(ctx, "pfks_digits_tc_kernel"));
-    dim3 grid(ctx->G() * (W / TC_NT), mpad / TC_MT);
-    lwe_gemm_tc_kernel<2><<<grid, 256, 0, ctx->stream>>>(DA, nct, mpad, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, nullptr, 0, ggsw);
-    TRY(post_launch(ctx, "lwe_gemm_tc_kernel<2>"));
+    TRY(post_launch(ctx, "umma_digit_tiles_kernel(pfks)"));
+    TRY(gemm_umma<2>(ctx, DA, nct, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, nullptr, 0, ggsw));
     pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), kFixCap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
     return post_launch(ctx, "pfks_fixup_kernel");
 }
@@ -419,11 +425,12 @@ int tac_ctx_alloc_keys(tac_ctx* ctx) {
     CU(cudaMalloc(&ctx->ks_corr, (size_t)(ctx->p.n + 1) * 8));
     CU(cudaMalloc(&ctx->pfks_corr, (size_t)ctx->G() * ctx->G() * ctx->p.N * 8));
     {
-        const int Kd = (ctx->big() + 1) * ctx->p.pfks_l, nkb = (Kd + TC_KB - 1) / TC_KB;
-        CU(cudaMalloc(&ctx->pfks_planes, (size_t)ctx->G() * nkb * TC_KB * ctx->G() * ctx->p.N * 8));
+        const int Kd = (ctx->big() + 1) * ctx->p.pfks_l, nkb = (Kd + UG_KB - 1) / UG_KB;
+        const int W = ctx->G() * ctx->p.N, tiles = (W + UG_NT - 1) / UG_NT;
+        CU(cudaMalloc(&ctx->pfks_planes, (size_t)ctx->G() * tiles * nkb * UG_B_BYTES));
         CU(cudaMalloc(&ctx->pfks_fix, 8 + (size_t)kFixCap * 8));
-        const int Kd_ks = ctx->big() * ctx->p.ks_l, nkb_ks = (Kd_ks + TC_KB - 1) / TC_KB, tiles_ks = (ctx->p.n + 1 + TC_NT - 1) / TC_NT;
-        CU(cudaMalloc(&ctx->ks_planes, (size_t)nkb_ks * tiles_ks * 8 * 2 * TC_NT * 16));
+        const int Kd_ks = ctx->big() * ctx->p.ks_l, nkb_ks = (Kd_ks + UG_KB - 1) / UG_KB, tiles_ks = (ctx->p.n + 1 + UG_NT - 1) / UG_NT;
+        CU(cudaMalloc(&ctx->ks_planes, (size_t)tiles_ks * nkb_ks * UG_B_BYTES));
     }
     ctx->keys_allocated = true;
     return TAC_OK;
@@ -459,15 +466,15 @@ int tac_ctx_keys_ready(tac_ctx* ctx) {
     negate_kernel<<<grid1d(W * ctx->G(), 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfks_corr, W * ctx->G());
     TRY(post_launch(ctx, "negate_kernel"));
     CU(cudaStreamSynchronize(ctx->stream));
-    {   // byte planes of the PFPKSK for the tensor-core GEMM
-        const int nkb = (Kd_pf + TC_KB - 1) / TC_KB;
-        const size_t units = (size_t)ctx->G() * nkb * (W / TC_NT) * 2 * TC_NT;
-        pfks_key_planes_kernel<<<grid1d(units, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfpksk, ctx->G(), Kd_pf, (int)W, nkb, ctx->pfks_planes);
-        TRY(post_launch(ctx, "pfks_key_planes_kernel"));
-        const int nkb_ks = (Kd_ks + TC_KB - 1) / TC_KB, tiles_ks = (p.n + 1 + TC_NT - 1) / TC_NT;
-        const size_t units_ks = (size_t)nkb_ks * tiles_ks * 2 * TC_NT;
-        pfks_key_planes_kernel<<<grid1d(units_ks, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->ksk, 1, Kd_ks, p.n + 1, nkb_ks, ctx->ks_planes);
-        TRY(post_launch(ctx, "ks_key_planes_kernel"));
+    {   // byte-plane tiles of the PFPKSK and the KSK for the tcgen05 GEMM
+        const int nkb = (Kd_pf + UG_KB - 1) / UG_KB, tiles = ((int)W + UG_NT - 1) / UG_NT;
+        const size_t units = (size_t)ctx->G() * tiles * nkb * 2 * UG_NT;
+        umma_key_tiles_kernel<<<grid1d(units, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->pfpksk, ctx->G(), Kd_pf, (int)W, nkb, ctx->pfks_planes);
+        TRY(post_launch(ctx, "umma_key_tiles_kernel(pfks)"));
+        const int nkb_ks = (Kd_ks + UG_KB - 1) / UG_KB, tiles_ks = (p.n + 1 + UG_NT - 1) / UG_NT;
+        const size_t units_ks = (size_t)tiles_ks * nkb_ks * 2 * UG_NT;
+        umma_key_tiles_kernel<<<grid1d(units_ks, 256, ctx->sm_count), 256, 0, ctx->stream>>>(ctx->ksk, 1, Kd_ks, p.n + 1, nkb_ks, ctx->ks_planes);
+        TRY(post_launch(ctx, "umma_key_tiles_kernel(ks)"));
         CU(cudaStreamSynchronize(ctx->stream));
     }
     ctx->keys_valid = true;

@@ -1,0 +1,289 @@
+// kernels_gemm_umma.cuh — the private functional packing keyswitch as an exact integer GEMM on the 5th-generation tensor
+// cores (tcgen05.mma kind::i8, accumulators in tensor memory), fed by bulk asynchronous copies through an mbarrier pipeline.
+//
+//   out[ct][j][col] = corr[j][col] − Σ_k d'[ct][k]·key[j][k][col]   (mod 2^64)          reference: [U] tfhe
+//   lwe_private_functional_packing_keyswitch.rs, M = ciphertexts, K = (kN+1)·l digits, N = (k+1)·(k+1)N columns
+//
+// Exactness: both operands are split into unsigned byte limbs, d' = a0 + 2^8·a1 (d' ∈ [0, 2^16); the lone value 2^16 is
+// patched by pfks_fixup_kernel) and key = Σ_{b<8} 2^(8b)·key_b.  Only limb pairs of weight w = a + b < 8 matter mod 2^64:
+// 15 u8×u8→s32 MMAs per k-block, accumulated BY WEIGHT into 8 tensor-memory accumulators (each partial sum stays below
+// 2·4128·255² < 2^31), recombined with shifts in the epilogue.
+//
+// One CTA = 128 ciphertexts × 64 columns: 8 weights × 64 columns = all 512 TMEM columns.  Roles (6 warps):
+//   warp 0  lane 0: producer — one cp.async.bulk per operand tile and k-block into a ring of stages, completion on full[s]
+//   warp 1  lane 0: MMA issuer — waits full[s], issues the 15 (8 with one digit limb) tcgen05.mma of the k-block,
+//                   tcgen05.commit → empty[s]; after the last k-block commit → accum
+//   warps 2-5: epilogue — tcgen05.ld the 8 weight accumulators of their 32 TMEM lanes, recombine, subtract from corr, store
+//
+// Operand tiles are prepared in global memory in exactly the shared-memory image the MMA descriptors expect (K-major, no
+// swizzle: 8-row × 16-byte core matrices, 128 B each), so one contiguous bulk copy per tile suffices — no tensor maps:
+//   A tiles  [m tile][kb][limb][k half][row 128][16 B]              (NLIMB·4 KB per k-block; core-matrix strides: K 2048 B, M 128 B)
+//   B tiles  [key j][n tile][kb][byte b 8][k half][col 64][16 B]    (16 KB per k-block;      core-matrix strides: K 1024 B, N 128 B)
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "tac_common.h"
+
+namespace tac {
+
+constexpr int UG_KB = 32;            // k per block = K of one kind::i8 MMA
+constexpr int UG_MT = 128;           // ciphertexts per CTA (UMMA M)
+constexpr int UG_NT = 64;            // columns per CTA (UMMA N)
+constexpr int UG_B_BYTES = 8 * 2 * UG_NT * 16;               // 16 KB
+constexpr int UG_THREADS = 192;
+template <int NLIMB> struct UgCfg {
+    static constexpr int A_BYTES = NLIMB * 2 * UG_MT * 16;   // 4 KB per limb
+    static constexpr int STAGE_BYTES = A_BYTES + UG_B_BYTES;
+    static constexpr int STAGES = NLIMB == 2 ? 8 : 9;        // 8 × 24 KB = 192 KB, 9 × 20 KB = 180 KB
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 1024;      // + barriers, + alignment slack
+};
+
+// ---------------------------------------------------------------------------------------------- operand preparation
+// Digits: exact decomposition (closest_representable + iterator), biased by B/2 to d' >= 0, byte limbs.  One thread
+// produces 16 consecutive k of one ciphertext.  ks_mode 0: PFKS (closest_representable first; storage index s ↔ level s+1, two limbs); 1: LWE keyswitch (mask elements only, storage index s ↔ level l-s, one limb).
+__global__ void umma_digit_tiles_kernel(const uint64_t* __restrict__ in, int nct, int mpad, int in_stride, int b, int l, int Kd, int nkb, int ks_mode,
+                                        uint8_t* __restrict__ DA, uint32_t* __restrict__ fix_count, uint2* __restrict__ fix_list, uint32_t fix_cap) {
+    const int nlimb = ks_mode ? 1 : 2;
+    const size_t total = (size_t)mpad * nkb * 2;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int ct = (int)(idx % mpad);
+        const size_t q = idx / mpad;
+        const int khalf = (int)(q & 1), kb = (int)(q >> 1);
+        uint32_t lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+        if (ct < nct) {
+#pragma unroll
+            for (int kq = 0; kq < 16; kq++) {
+                const int k = kb * UG_KB + khalf * 16 + kq;
+                if (k >= Kd) continue;
+                const int i = k / l, lev = ks_mode ? l - (k - i * l) : k - i * l + 1;
+                const uint64_t x = in[(size_t)ct * in_stride + i];
+                uint64_t st = decomp_init_state(ks_mode ? x : closest_representable(x, b, l), b, l);
+                int64_t d = 0;
+                for (int q2 = l; q2 >= lev; q2--) d = decomp_next(st, b);
+                uint32_t dp = (uint32_t)(d + (int64_t)(1u << (b - 1)));
+                if (dp >> 16) {                                   // d' == 2^16: patched by pfks_fixup_kernel
+                    const uint32_t slot = atomicAdd(fix_count, 1u);
+                    if (slot < fix_cap) fix_list[slot] = make_uint2((uint32_t)ct, (uint32_t)k);
+                    dp = 0;
+                }
+                lo[kq >> 2] |= (dp & 0xFFu) << (8 * (kq & 3));
+                hi[kq >> 2] |= (dp >> 8) << (8 * (kq & 3));
+            }
+        }
+        const int mt = ct / UG_MT, row = ct - mt * UG_MT;
+        uint8_t* tile = DA + ((size_t)mt * nkb + kb) * (size_t)(nlimb * 2 * UG_MT * 16);
+        *reinterpret_cast<uint4*>(tile + ((size_t)(0 * 2 + khalf) * UG_MT + row) * 16) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        if (!ks_mode) *reinterpret_cast<uint4*>(tile + ((size_t)(1 * 2 + khalf) * UG_MT + row) * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    }
+}
+// Key byte planes (once per key upload).  key: [nkeys][Kd][W] words.
+__global__ void umma_key_tiles_kernel(const uint64_t* __restrict__ key, int nkeys, int Kd, int W, int nkb, uint8_t* __restrict__ KP) {
+    const int ntiles = (W + UG_NT - 1) / UG_NT;
+    const size_t total = (size_t)nkeys * ntiles * nkb * 2 * UG_NT;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
+        const int n = (int)(idx % UG_NT);
+        size_t q = idx / UG_NT;
+        const int khalf = (int)(q & 1); q >>= 1;
+        const int kb = (int)(q % nkb); q /= nkb;
+        const int tile = (int)(q % ntiles);
+        const int j = (int)(q / ntiles);
+        uint32_t pl[8][4];
+#pragma unroll
+        for (int bb = 0; bb < 8; bb++) { pl[bb][0] = pl[bb][1] = pl[bb][2] = pl[bb][3] = 0; }
+#pragma unroll
+        for (int kq = 0; kq < 16; kq++) {
+            const int k = kb * UG_KB + khalf * 16 + kq;
+            const uint64_t v = (k < Kd && tile * UG_NT + n < W) ? key[((size_t)j * Kd + k) * W + tile * UG_NT + n] : 0ull;
+#pragma unroll
+            for (int bb = 0; bb < 8; bb++) pl[bb][kq >> 2] |= (uint32_t)((v >> (8 * bb)) & 0xFFull) << (8 * (kq & 3));
+        }
+        uint8_t* base = KP + (((size_t)j * ntiles + tile) * nkb + kb) * (size_t)UG_B_BYTES;
+#pragma unroll
+        for (int bb = 0; bb < 8; bb++)
+            *reinterpret_cast<uint4*>(base + (((size_t)bb * 2 + khalf) * UG_NT + n) * 16) = make_uint4(pl[bb][0], pl[bb][1], pl[bb][2], pl[bb][3]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- PTX helpers
+namespace ug {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): start address, leading-dimension
+// byte offset (between core matrices adjacent in K), stride-dimension byte offset (adjacent in M/N), all >> 4; version 1.
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor) for kind::i8: D = s32, A/B = unsigned 8-bit, both K-major
+__device__ __forceinline__ constexpr uint32_t idesc_u8(int M, int N) { return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24); }
+__device__ __forceinline__ void mma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+}
+}  // namespace ug
+
+// ---------------------------------------------------------------------------------------------- the GEMM
+// grid.x = m tiles × n tiles × keys in a raster that keeps GM consecutive m tiles on one B tile (L2 reuse of both operands).
+// out[(ct·nkeys + j)·W + col] = corr[j·W + col] − Σ  (+ last_col_add[ct·add_stride] on column W-1: the LWE body of the keyswitch)
+template <int NLIMB>
+__global__ void __launch_bounds__(UG_THREADS, 1)
+lwe_gemm_umma_kernel(const uint8_t* __restrict__ DA, int nct, int mtiles, const uint8_t* __restrict__ KP, int W, int nkeys, int nkb,
+                     const uint64_t* __restrict__ corr, const uint64_t* __restrict__ last_col_add, size_t add_stride, uint64_t* __restrict__ out) {
+    typedef UgCfg<NLIMB> Cfg;
+    extern __shared__ __align__(16) unsigned char ug_smem_raw[];
+    const uint32_t raw = ug::smem_u32(ug_smem_raw);
+    const uint32_t base = (raw + 127u) & ~127u;                                   // core matrices are 128 B
+    const uint32_t bars = base + Cfg::STAGES * Cfg::STAGE_BYTES;                  // full[S], empty[S], accum, tmem slot
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (Cfg::STAGES + s); };
+    const uint32_t accum_bar = bars + 8u * (2 * Cfg::STAGES);
+    const uint32_t tmem_slot = accum_bar + 8u;
+    volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(ug_smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ntiles = (W + UG_NT - 1) / UG_NT;
+    // raster: groups of GM m tiles sweep all (key, n tile) pairs
+    constexpr int GM = 8;
+    const int ncols = ntiles * nkeys;
+    int t = blockIdx.x;
+    const int group = t / (GM * ncols);
+    const int gm = min(GM, mtiles - group * GM);
+    t -= group * GM * ncols;
+    const int colt = t / gm, mt = group * GM + (t - colt * gm);
+    const int j = colt / ntiles, tile = colt - j * ntiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < Cfg::STAGES; s++) { ug::mbar_init(full_bar(s), 1); ug::mbar_init(empty_bar(s), 1); }
+        ug::mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot_ptr;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const uint8_t* a_src = DA + (size_t)mt * nkb * Cfg::A_BYTES;
+            const uint8_t* b_src = KP + ((size_t)j * ntiles + tile) * nkb * (size_t)UG_B_BYTES;
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % Cfg::STAGES;
+                if (kb >= Cfg::STAGES) ug::mbar_wait(empty_bar(s), ((kb / Cfg::STAGES) - 1) & 1);
+                ug::mbar_expect_tx(full_bar(s), Cfg::STAGE_BYTES);
+                const uint32_t dst = base + s * Cfg::STAGE_BYTES;
+                ug::bulk_g2s(dst, a_src + (size_t)kb * Cfg::A_BYTES, Cfg::A_BYTES, full_bar(s));
+                ug::bulk_g2s(dst + Cfg::A_BYTES, b_src + (size_t)kb * UG_B_BYTES, UG_B_BYTES, full_bar(s));
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = ug::idesc_u8(UG_MT, UG_NT);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % Cfg::STAGES;
+                ug::mbar_wait(full_bar(s), (kb / Cfg::STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a0 = base + s * Cfg::STAGE_BYTES, b0 = a0 + Cfg::A_BYTES;
+#pragma unroll
+                for (int bb = 0; bb < 8; bb++) {
+                    const uint64_t db = ug::smem_desc(b0 + bb * (2 * UG_NT * 16), UG_NT * 16, 128);
+#pragma unroll
+                    for (int limb = 0; limb < NLIMB; limb++) {
+                        const int w = bb + limb;
+                        if (w >= 8) continue;
+                        const uint64_t da = ug::smem_desc(a0 + limb * (2 * UG_MT * 16), UG_MT * 16, 128);
+                        // In issue order the first contribution to weight w is (byte 0, limb 0) for w = 0 and, with two
+                        // limbs, (byte w-1, limb 1) for w >= 1 (with one limb: (byte w, limb 0)): that MMA of k-block 0 overwrites.
+                        const bool first = (kb == 0) && (NLIMB == 1 || limb == 1 || bb == 0);
+                        ug::mma_i8(tmem_base + (uint32_t)(w * UG_NT), da, db, idesc, first ? 0u : 1u);
+                    }
+                }
+                ug::mma_commit(empty_bar(s));                      // frees the stage when these MMAs have read it
+            }
+            ug::mma_commit(accum_bar);
+        }
+    } else {
+        // epilogue warps 2..5 own TMEM lanes 32·(warp % 4) … +31 = rows of the tile
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int ct = mt * UG_MT + row;
+        ug::mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint64_t* cj = corr + (size_t)j * W;
+#pragma unroll 1
+        for (int c0 = 0; c0 < UG_NT; c0 += 8) {
+            uint32_t r[8][8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) ug::tmem_ld8(lane_addr + (uint32_t)(w * UG_NT + c0), r[w]);
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int col = tile * UG_NT + c0;
+            if (ct < nct && col < W) {
+                uint64_t v[8];
+#pragma unroll
+                for (int e = 0; e < 8; e++) {
+                    uint64_t sum = 0;
+#pragma unroll
+                    for (int w = 0; w < 8; w++) sum += (uint64_t)r[w][e] << (8 * w);
+                    v[e] = (col + e < W ? cj[col + e] : 0ull) - sum;
+                    if (last_col_add && col + e == W - 1) v[e] += last_col_add[(size_t)ct * add_stride];
+                }
+                uint64_t* dst = out + ((size_t)ct * nkeys + j) * W + col;
+                if (col + 8 <= W && ((((size_t)ct * nkeys + j) * W + col) & 1) == 0) {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) *reinterpret_cast<ulonglong2*>(dst + e) = make_ulonglong2(v[e], v[e + 1]);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e++) if (col + e < W) dst[e] = v[e];
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+}
+
+// ---- patch for digits d' == 2^16 (digit = +B/2, exact ties only): out[ct][j][:] −= 2^16 · key[j][k][:]
+__global__ void pfks_fixup_kernel(const uint32_t* __restrict__ fix_count, const uint2* __restrict__ fix_list, uint32_t fix_cap,
+                                  const uint64_t* __restrict__ key, int Kd, int W, int nkeys, uint64_t* __restrict__ out) {
+    const uint32_t n = min(*fix_count, fix_cap);
+    for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
+        const uint2 f = fix_list[e];
+        for (int idx = threadIdx.x; idx < nkeys * W; idx += blockDim.x) {
+            const int j = idx / W, col = idx - j * W;
+            const uint64_t v = key[((size_t)j * Kd + f.y) * W + col] << 16;
+            atomicAdd(reinterpret_cast<unsigned long long*>(out + ((size_t)f.x * nkeys + j) * W + col), (unsigned long long)(0ull - v));
+        }
+    }
+}
+
+}  // namespace tac

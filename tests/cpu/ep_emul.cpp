@@ -72,7 +72,7 @@ template <int L> static void digits_t(uint64_t x, int b, double* out) {
 extern "C" {
 int emul_cmux_step(int N, int K, int L, int B, int NT, const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
 #define CASE(n, k, l, b, nt) if (N == n && K == k && L == l && B == b && NT == nt) { emul_step<n, k, l, b, nt>(ggsw_std, base_log, rot, acc); return 0; }
-    CASE(512, 4, 3, 4, 320) CASE(512, 4, 3, 2, 256) CASE(512, 4, 1, 4, 320) CASE(512, 4, 1, 1, 256)
+    CASE(512, 4, 3, 3, 256) CASE(512, 4, 3, 4, 320) CASE(512, 4, 3, 2, 256) CASE(512, 4, 1, 3, 256) CASE(512, 4, 1, 4, 320) CASE(512, 4, 1, 1, 256)
     CASE(1024, 2, 2, 2, 256) CASE(1024, 2, 4, 2, 256) CASE(1024, 2, 1, 2, 256) CASE(1024, 2, 1, 1, 96)
 #undef CASE
     return -1;

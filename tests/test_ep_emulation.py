@@ -77,7 +77,8 @@ def _rot_diff(a, r, N):
 
 
 CASES = [  # (preset, N, K, L, base_log, B, NT) — the kernel instantiations of capi.cu
-    (64, 512, 4, 3, 12, 4, 320), (64, 512, 4, 3, 12, 2, 256), (64, 512, 4, 1, 13, 4, 320), (64, 512, 4, 1, 13, 1, 256),
+    (64, 512, 4, 3, 12, 3, 256), (64, 512, 4, 3, 12, 4, 320), (64, 512, 4, 3, 12, 2, 256), (64, 512, 4, 1, 13, 3, 256), (64, 512, 4, 1, 13, 4, 320),
+    (64, 512, 4, 1, 13, 1, 256),
     (4, 1024, 2, 2, 15, 2, 256), (256, 1024, 2, 4, 9, 2, 256), (4, 1024, 2, 1, 11, 2, 256), (4, 1024, 2, 1, 11, 1, 96)]
 
 

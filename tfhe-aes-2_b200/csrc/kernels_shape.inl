@@ -67,7 +67,10 @@ cudaError_t launch_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_i
 cudaError_t s_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
                  const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
 #if TAC_N == 512
-    if (n_out >= 4) return launch_vp<4, 320>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    // 3 outputs per CTA with 256 threads (222 registers, no spills) measured 20 % faster on B200 than 4 outputs with 320
+    // threads (168-register cap, spills) and 28 % faster than 2 outputs with 160 threads
+    if (n_out >= 3) return launch_vp<3, 256>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    if (n_out == 2) return launch_vp<2, 160>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
 #endif
     return launch_vp<1, 128>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
 }

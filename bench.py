@@ -182,6 +182,16 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def pbs_traffic(n_ct):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one pbs_kernel launch from the committed ncu --set full captures
+    (profiles/pbs_dram_traffic.json: ciphertexts per launch → bytes); None when no capture exists for this launch size."""
+    try:
+        table = json.load(open(os.path.join(ROOT, "profiles", "pbs_dram_traffic.json")))
+        return table.get(str(n_ct))
+    except Exception:
+        return None
+
+
 def workload_config(args, cpu=False):
     return {"workload": f"AES-128 CTR stream, {args.blocks} counter blocks per GPU x 10 rounds (per-GPU shard of BASELINE config 5: 1024 blocks / 8 GPUs), "
                         "params_sqrd_lvl_64, key schedule precomputed", "blocks_per_gpu": args.blocks, "rounds": 10,
@@ -337,7 +347,7 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(out_host.numel() * 8 * world), "steps": e2e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "kernel": "pbs_kernel<N=512,k=4,l=3,B=3,256 threads>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": pbs_traffic(int(n_ct_per_launch)),
                          "peak_source": "DFMA microbenchmark in this run (FP64 is not in MEASURED_PEAKS.json; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                          "algorithmic_flop_per_launch": n_ct_per_launch * FLOP_PER_PBS, "avg_launch_ms": pbs_ms, "launches": int(pbs_launches),
                          "whole_step_frac": value / world * FLOP_PER_BLOCK / 1e12 / fp64_peak if fp64_peak else None},

@@ -140,11 +140,56 @@ TAC_HD constexpr int slot_of(int q, int i) { return q * 16 + (i ^ (q & 15)); }
 // twiddle.  One table serves both directions:
 //     wT[slot_of(q, t)] = e^{iπt/N} · e^{-2πi·tq/M}            (M entries, swizzled like S so that both the pass-1
 //                                                                 (t across lanes) and pass-A (q across lanes) reads are conflict-free)
+// Memory-operation order.  All buffers of a CTA are carved from one dynamic shared-memory array, so the compiler must
+// assume that a store to one of them may alias a later load from another and keeps them in program order: a loop of the
+// form "load – compute – store" is executed strictly one element at a time and exposes the shared-memory latency every
+// time (measured: 16 serialised twiddle loads ≈ 400 cycles of a 1550-cycle pass, tools/fft_lat.cu; PBS kernel 119.4 → 113.4 ms).  The passes below are
+// therefore written in CHUNKS: all loads of a chunk first, then the arithmetic and the stores of the chunk.
+constexpr int kChunk = 8;        // twiddles per chunk (32 registers in flight); measured on B200: 8 → 113.4 ms, 4 or 16 → 116.5 ms
+constexpr int kLoadChunk = 4;    // operand pairs per chunk of the decomposing pass (2, 4, 8, 16 measure the same)
+
+// S[slot] = v[i] · wT[slot] (forward) for the P registers of thread t, chunked
+template <int P, bool CONJ, class SlotFn>
+TAC_HD void twiddle_store(const cplx* v, SlotFn slot, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+    constexpr int CH = P < kChunk ? P : kChunk;
+    static_for<0, P, CH>([&](auto cc) {
+        constexpr int c0 = decltype(cc)::value;
+        cplx w[CH];
+        static_for<0, CH>([&](auto kc) { constexpr int k = decltype(kc)::value; w[k] = wT[slot(c0 + k)]; });
+        static_for<0, CH>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            if constexpr (CONJ) { if constexpr (c0 + k == 0) S[slot(0)] = v[0]; else S[slot(c0 + k)] = cmul_conj(v[c0 + k], w[k]); }
+            else S[slot(c0 + k)] = cmul(v[c0 + k], w[k]);
+        });
+    });
+}
 // ------------------------------------------------------------------------------------------------ forward, pass 1
-// `src(jj, a, b)` yields the real samples jj and jj + M (0 <= jj < M) as doubles.  Thread t (0..15) of the FFT group.
+// Two-phase source: `load(jj)` fetches whatever the samples jj and jj + M (0 <= jj < M) are made from (its loads are
+// batched per chunk), `finish(jj, raw, a, b)` turns it into the two real samples (and may store by-products).
+// Thread t (0..15) of the FFT group.
+template <int N, class Load, class Finish>
+TAC_HD void fft_fwd_pass1_2ph(int t, Load load, Finish finish, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;     // c_m = exp(+2πi · m·CSTEP / 128)
+    constexpr int CH = kLoadChunk;
+    cplx v[P];
+    static_for<0, P, CH>([&](auto cc) {
+        constexpr int c0 = decltype(cc)::value;
+        decltype(load(0)) raw[CH];
+        static_for<0, CH>([&](auto kc) { constexpr int k = decltype(kc)::value; raw[k] = load(t + 16 * (c0 + k)); });
+        static_for<0, CH>([&](auto kc) {
+            constexpr int k = decltype(kc)::value, m = c0 + k;
+            double a, b;
+            finish(t + 16 * m, raw[k], a, b);
+            v[m] = mul_w128<true, m * CSTEP>(mk(a, b));
+        });
+    });
+    dft_fwd<P>(v);
+    twiddle_store<P, false>(v, [&](int i) { return slot_of(bitrev<P>(i), t); }, wT, S);
+}
+// `src(jj, a, b)` yields the real samples jj and jj + M directly (sources without by-product stores)
 template <int N, class Src>
 TAC_HD void fft_fwd_pass1(int t, Src src, const cplx* __restrict__ wT, cplx* __restrict__ S) {
-    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;     // c_m = exp(+2πi · m·CSTEP / 128)
+    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;
     cplx v[P];
     static_for<0, P>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
@@ -153,11 +198,7 @@ TAC_HD void fft_fwd_pass1(int t, Src src, const cplx* __restrict__ wT, cplx* __r
         v[m] = mul_w128<true, m * CSTEP>(mk(a, b));
     });
     dft_fwd<P>(v);
-    static_for<0, P>([&](auto ic) {
-        constexpr int i = decltype(ic)::value;
-        const int sl = slot_of(bitrev<P>(i), t);
-        S[sl] = cmul(v[i], wT[sl]);
-    });
+    twiddle_store<P, false>(v, [&](int i) { return slot_of(bitrev<P>(i), t); }, wT, S);
 }
 // ------------------------------------------------------------------------------------------------ forward, pass 2 (in place)
 template <int N>
@@ -182,11 +223,7 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
         cplx v[16];
         static_for<0, 16>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = S[slot_of(q, i)]; });
         dft_inv<16>(v);
-        static_for<0, 16>([&](auto tc) {
-            constexpr int tt = decltype(tc)::value;
-            const int sl = slot_of(q, tt);
-            if constexpr (tt == 0) S[sl] = v[tt]; else S[sl] = cmul_conj(v[tt], wT[sl]);
-        });
+        twiddle_store<16, true>(v, [&](int tt) { return slot_of(q, tt); }, wT, S);
     }
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass B

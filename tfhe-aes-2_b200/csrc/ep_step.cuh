@@ -21,6 +21,7 @@
 #pragma once
 #include "ep_core.cuh"
 
+
 #include <cmath>
 
 namespace tac {
@@ -71,13 +72,15 @@ template <class C, class CoefFn>
 TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
                             cplx* __restrict__ S) {
     uint32_t* dj = dig + (size_t)job * (C::L - 1) * C::M;
-    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) {
-        uint32_t w[C::L];
-        decompose_pair<C::L>(coef(jj), coef(jj + C::M), dc, w);
+    struct Pair { uint64_t x0, x1; };
+    fft_fwd_pass1_2ph<C::N>(t, [&](int jj) { Pair p; p.x0 = coef(jj); p.x1 = coef(jj + C::M); return p; },
+        [&](int jj, const Pair& p, double& a, double& b) {
+            uint32_t w[C::L];
+            decompose_pair<C::L>(p.x0, p.x1, dc, w);
 #pragma unroll
-        for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
-        unpack_digits(w[C::L - 1], dc, a, b);
-    }, wT, S + (size_t)job * C::M);
+            for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
+            unpack_digits(w[C::L - 1], dc, a, b);
+        }, wT, S + (size_t)job * C::M);
 }
 // forward FFT pass 1 of the cached level-`lev` digits (lev < L)
 template <class C>

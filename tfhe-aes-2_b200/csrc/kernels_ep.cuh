@@ -53,6 +53,13 @@ struct EpSmem {
 #ifndef TAC_EP_DBG
 #define TAC_EP_DBG 0
 #endif
+// TAC_EP_TIMING (development only): thread 0 of CTA 0 accumulates clock64() deltas per phase of the step into tac_ep_times
+#ifdef TAC_EP_TIMING
+__device__ long long tac_ep_times[32];
+#define TAC_EP_T(k) do { if (tid == 0 && blockIdx.x == 0) { const long long now_ = clock64(); tac_ep_times[k] += now_ - tac_tprev; tac_tprev = now_; } } while (0)
+#else
+#define TAC_EP_T(k) do { } while (0)
+#endif
 template <class C, int NT, int MAC_DEPTH = 5, class CoefFn>
 __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, const cplx* __restrict__ ggsw, CoefFn coef, int base_log,
                                                cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G]) {
@@ -66,6 +73,9 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     // (A variant that ping-pongs between two FFT buffers, so that mac(l) and the transforms of level l-1 share one barrier
     // interval — L+1 barriers instead of 2L — measured 3 % SLOWER on B200 (tools/pbs_bench.cu, 123.2 vs 119.4 ms for 6144
     // ciphertexts) and costs 61 KB more shared memory; the single-buffer schedule below is the one that ships.)
+#ifdef TAC_EP_TIMING
+    long long tac_tprev = clock64();
+#endif
     if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, dc, sm.dig, sm.wT, sm.S);
     if (active && !DO_FWD && DO_DEC) {          // decomposition alone
         for (int m = 0; m < C::M / 16; m++) {
@@ -77,28 +87,40 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
         }
     }
     if (active && DO_FWD && !DO_DEC) grp_fwd1<C>(t, job, 1, dc, sm.dig, sm.wT, sm.S);
+    TAC_EP_T(0);
     if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);                 // in flight during pass 2 and the barrier
     __syncwarp();
     if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
+    TAC_EP_T(1);
     __syncthreads();
+    TAC_EP_T(2);
     if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, C::L, ggsw, sm.S, out, g);
     if (C::L == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);         // own slots only: no barrier needed in between
+    TAC_EP_T(3);
     __syncthreads();
+    TAC_EP_T(4);
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
         if (active && DO_FWD) grp_fwd1<C>(t, job, lev, dc, sm.dig, sm.wT, sm.S);
+        TAC_EP_T(5);
         if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
         __syncwarp();
         if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
+        TAC_EP_T(6);
         __syncthreads();
+        TAC_EP_T(7);
         if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, ggsw, sm.S, out, g);
         if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);
+        TAC_EP_T(8);
         __syncthreads();
+        TAC_EP_T(9);
     }
     if (active && DO_INV) grp_inv1<C>(t, job, sm.wT, sm.S);
     __syncwarp();
+    TAC_EP_T(10);
     if (active && DO_INV) grp_inv2<C>(t, job, sm.S, sm.acc);
     __syncwarp();
+    TAC_EP_T(11);
 }
 
 // [U] glwe_sample_extraction.rs::extract_lwe_sample_from_glwe_ciphertext(.., MonomialDegree(0)); element e of the LWE

@@ -38,10 +38,10 @@ cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, 
     // B ciphertexts per CTA share every BSK load; fewer per CTA when the batch cannot fill the GPU otherwise
     // Measured on B200 (profiles/): B = 3 with 256 threads (8 warps, 2 per scheduler, 255 registers, no spills) beats B = 4
     // with 320 threads (10 warps but a 168-register cap per scheduler partition and spills) by 27 %.
-    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
     // small batches (per-block latency): 256 threads also for 2 and 1 ciphertexts per CTA — every MAC thread then owns one
     // frequency slot and its key rows are all prefetched (16 % / 15 % faster than 160 / 128 threads, tools/pbs_bench.cu)
-    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
     return launch_pbs<L, 1, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation

@@ -68,6 +68,16 @@ void run(const char* name, const Bufs& b) {
     const double flop = (double)b.nct * n_lwe * 389120.0;
     printf("%-28s regs=%3d lmem=%4zu smem=%6zu occ=%d  best %8.3f ms  avg %8.3f ms  %6.2f TF/s  frac %.3f  %7.1f PBS/ms  sum=%016llx\n", name, fa.numRegs,
            (size_t)fa.localSizeBytes, smem, occ, best, tot / b.reps, flop / (best * 1e-3) / 1e12, flop / (best * 1e-3) / 1e12 / b.peak, b.nct / best, h);
+#ifdef TAC_EP_TIMING
+    {   // per-phase clock attribution (thread 0 of CTA 0; build with -DTAC_EP_TIMING)
+        long long tt[32]; CK(cudaMemcpyFromSymbol(tt, tac_ep_times, sizeof(tt)));
+        const double steps = (double)n_lwe * (b.reps + 1);                       // CTA 0 runs once per launch
+        const char* nm[12] = {"decomp+fwd1(L)", "fwd2(L)", "barrier", "mac(L)", "barrier", "fwd1(l<L)", "fwd2(l<L)", "barrier", "mac(l<L)", "barrier", "inv1", "inv2+acc"};
+        double tot2 = 0; for (int i = 0; i < 12; i++) tot2 += tt[i] / steps;
+        printf("   thread 0 cycles/step (%.0f):", tot2); for (int i = 0; i < 12; i++) printf(" %s=%.0f", nm[i], tt[i] / steps); printf("\n");
+        long long z[32] = {0}; CK(cudaMemcpyToSymbol(tac_ep_times, z, sizeof(z)));
+    }
+#endif
     fflush(stdout);
 }
 

@@ -23,3 +23,6 @@ PY
 echo "round starts at launch $SKIP" >> gpurun_out/ncu_launches_$TAG.log
 timeout 900 ncu --set full --clock-control none --import-source on --launch-skip $SKIP --launch-count 9 -f -o gpurun_out/prof_round_$TAG $CMD > gpurun_out/ncu_full_$TAG.log 2>&1
 tail -3 gpurun_out/ncu_full_$TAG.log
+# condensed evidence next to the report; KEEP_REP=0 drops the (≈ 40 MB) report itself — gpurun copies back at most 64 MiB
+python tools/ncu_summary.py gpurun_out/prof_round_$TAG.ncu-rep gpurun_out/round_$TAG > /dev/null
+if [ "${KEEP_REP:-1}" = "0" ]; then rm -f gpurun_out/prof_round_$TAG.ncu-rep; fi

@@ -194,6 +194,140 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
     }
 }
 
+// ================================================================================================ PBS, level-parallel variant
+// For small batches (per-block latency) the step of pbs_kernel is a chain of dependent phases executed by one 16-thread
+// group per polynomial: decompose → L × (forward FFT → MAC) → inverse FFT.  Here the L levels are transformed AT THE SAME
+// TIME by L·B·G groups (one FFT buffer per level), the decomposition of a polynomial is split over L groups, and the MAC runs
+// once over all L·G key rows with one prefetch ring.  Same arithmetic in the same order as pbs_kernel — bit-identical
+// results — but 4 barriers and one FFT latency per step instead of 2L barriers and L FFT latencies.
+//   P0  group (part, job): digits of all levels for its share of the coefficient pairs      ── barrier ──
+//   P1  group (level, job): forward FFT of that level from the cached digits                 ── barrier ──
+//   P2  256 slot threads: out = Σ_{level, p} fft(digits) · BSK row, written to the level-1 buffer   ── barrier ──
+//   P3  group (0, job): inverse FFT + torus accumulate                                        ── barrier ──
+template <int N, int K, int L, int B, int NT, int MAC_DEPTH = 5>
+__global__ void __launch_bounds__(NT, 1)
+pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
+                const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
+    typedef EpCfg<N, K, L, B> C;
+    constexpr int JOBS = C::JOBS, ROWS = L * C::G, NMAC = C::M;
+    static_assert(NT / 16 >= L * JOBS, "one 16-thread group per (level, polynomial)");
+    static_assert(NT >= NMAC && MAC_DEPTH <= ROWS, "one MAC thread per frequency slot");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                    // [B][G][N]
+    cplx* S = reinterpret_cast<cplx*>(acc + C::acc_words);                     // [L][JOBS][M]   (storage index s ↔ level s+1)
+    uint32_t* dig = reinterpret_cast<uint32_t*>(S + (size_t)L * C::s_cplx);    // [JOBS][L][M]
+    cplx* wT = reinterpret_cast<cplx*>(dig + (size_t)JOBS * L * C::M);
+    int* rot_sm = reinterpret_cast<int*>(wT + C::M);                           // [2][B]
+    const int tid = threadIdx.x;
+    const int grp = tid >> 4, t = tid & 15;
+    const int part = grp / JOBS, job = grp - part * JOBS;                      // part: share of the pairs in P0, level index in P1
+    const bool active = grp < L * JOBS;
+    const int ct0 = blockIdx.x * B;
+    const int n1 = n + 1;
+    auto switched = [&](int b, int i) -> int {
+        const int ct = ct0 + b;
+        if (ct >= nct) return 0;
+        uint64_t a = __ldg(lwe_small + (size_t)ct * n1 + i);
+        if (i == n) a += (1ull << 62);
+        return modswitch(a, LogN<N>::v);
+    };
+    for (int i = tid; i < C::M; i += NT) wT[i] = g_wT[i];
+    if (tid < B) { rot_sm[tid] = switched(tid, 0); rot_sm[B + tid] = switched(tid, n); }
+    __syncthreads();
+    for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
+        const int b = idx / (C::G * N), rem = idx - b * C::G * N, p = rem / N, j = rem - p * N;
+        uint64_t v = 0;
+        if (p == K) {
+            const int s = (j + rot_sm[B + b]) & (2 * N - 1);
+            v = (s < N) ? (0ull - alpha) : alpha;
+        }
+        acc[idx] = v;
+    }
+    __syncthreads();
+    const DecompFast dc = make_decomp_fast(base_log, L);
+    const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    constexpr int P = C::M / 16;
+    const int m0 = part * P / L, m1 = (part + 1) * P / L;                     // this group's share of the P register rows
+    // key row r (MAC order: level L first, then L-1, …; polynomial p inside) of the step's GGSW
+    auto row_ptr = [&](const cplx* ggsw, int r) { return ggsw + (size_t)((L - 1 - r / C::G) * C::G + (r % C::G)) * C::G * C::M; };
+    for (int i = 0; i < n; i++) {
+        const int* rot = rot_sm + (i & 1) * B;
+        const cplx* ggsw = bsk + ggsw_sz * i;
+        if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+        // ---- P0: digits
+        if (active) {
+            const uint64_t* poly = acc + (size_t)job * N;
+            const int r = rot[job / C::G];
+            uint32_t* dj = dig + (size_t)job * L * C::M;
+#pragma unroll 2
+            for (int m = m0; m < m1; m++) {
+                const int jj = t + 16 * m;
+                uint32_t w[L];
+                decompose_pair<L>(rot_diff<N>(poly, jj, r), rot_diff<N>(poly, jj + C::M, r), dc, w);
+#pragma unroll
+                for (int s = 0; s < L; s++) dj[(size_t)s * C::M + jj] = w[s];
+            }
+        }
+        __syncthreads();
+        // ---- P1: forward FFT of level part+1 of polynomial job; the MAC threads request their first key rows
+        cplx g[MAC_DEPTH][C::G];
+        if (tid < NMAC) {
+#pragma unroll
+            for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, NMAC>(row_ptr(ggsw, r), 0, tid, g[r]);
+        }
+        {
+            const uint32_t* d = dig + ((size_t)job * L + part) * C::M;
+            cplx* Sj = S + ((size_t)part * JOBS + job) * C::M;
+            if (active) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, wT, Sj);
+            __syncwarp();                          // outside the predicate: a warp may hold one active and one idle group
+            if (active) fft_fwd_pass2<N>(t, Sj);
+        }
+        __syncthreads();
+        // ---- P2: Fourier MAC over all L·G key rows
+        if (tid < NMAC) {
+            cplx out[B][C::G];
+#pragma unroll
+            for (int b = 0; b < B; b++)
+#pragma unroll
+                for (int c = 0; c < C::G; c++) out[b][c] = mk(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int s = L - 1 - r / C::G, p = r % C::G;                  // storage index of the level, polynomial
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const cplx x = S[((size_t)s * JOBS + b * C::G + p) * C::M + tid];
+#pragma unroll
+                    for (int c = 0; c < C::G; c++) cfma(out[b][c], x, g[r % MAC_DEPTH][c]);
+                }
+                if (r + MAC_DEPTH < ROWS) mac_load_row<C, NMAC>(row_ptr(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
+            }
+            // every thread has finished READING its slot of all buffers only after the barrier; the result goes to rows
+            // of buffer 0 at this thread's own slot, which no other thread reads in P2
+#pragma unroll
+            for (int b = 0; b < B; b++)
+#pragma unroll
+                for (int c = 0; c < C::G; c++) S[(size_t)(b * C::G + c) * C::M + tid] = out[b][c];
+        }
+        __syncthreads();
+        // ---- P3: inverse FFT and accumulate (the groups of part 0)
+        if (active && part == 0) grp_inv1<C>(t, job, wT, S);
+        __syncwarp();
+        if (active && part == 0) grp_inv2<C>(t, job, S, acc);
+        __syncthreads();
+    }
+    constexpr int LW = K * N + 1;
+    for (int idx = tid; idx < B * LW; idx += NT) {
+        const int b = idx / LW, e = idx - b * LW, ct = ct0 + b;
+        if (ct >= nct) continue;
+        uint64_t v = sample_extract_elem<C>(acc + (size_t)b * C::G * N, e);
+        if (e == K * N) v += alpha;
+        out_big[(size_t)ct * LW + e] = v;
+    }
+}
+template <class C> struct WideSmem {
+    static constexpr size_t bytes = C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)C::M * 16 + 2 * C::B * sizeof(int) + 16;
+};
+
 // ================================================================================================ vertical packing
 // One CTA evaluates B outputs of one box (= one circuit_bootstrap call).  ggsw_f: [nbox][n_in][L][G][G][M].
 // The accumulator starts from init_glwe (CMux-tree result) when given, else from the trivial GLWE of LUT polynomial o.

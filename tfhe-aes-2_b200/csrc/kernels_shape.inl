@@ -32,17 +32,25 @@ cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, 
     pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
+template <int L, int DEPTH>
+cudaError_t launch_pbs_wide(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
+    typedef EpCfg<SN, SK, L, 1> C;
+    const size_t smem = WideSmem<C>::bytes;
+    TAC_SET_SMEM((pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH>), smem);
+    pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH><<<(unsigned)nct, 256, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    return cudaGetLastError();
+}
 template <int L>
 cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
 #if TAC_N == 512
-    // B ciphertexts per CTA share every BSK load; fewer per CTA when the batch cannot fill the GPU otherwise
-    // Measured on B200 (profiles/): B = 3 with 256 threads (8 warps, 2 per scheduler, 255 registers, no spills) beats B = 4
-    // with 320 threads (10 warps but a 168-register cap per scheduler partition and spills) by 27 %.
-    if (nct >= 3 * k.sm_count) return launch_pbs<L, 3, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
-    // small batches (per-block latency): 256 threads also for 2 and 1 ciphertexts per CTA — every MAC thread then owns one
-    // frequency slot and its key rows are all prefetched (16 % / 15 % faster than 160 / 128 threads, tools/pbs_bench.cu)
-    if (nct >= 2 * k.sm_count) return launch_pbs<L, 2, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
-    return launch_pbs<L, 1, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    // Two kernels, chosen by a wave-count cost model (times of one wave measured on B200, tools/pbs_bench.cu):
+    //  * pbs_kernel, 3 ciphertexts per CTA sharing every BSK load (255 registers, no spills; B = 4 with 320 threads hits a
+    //    168-register cap and is 27 % slower): 8.6 ms per wave of 3·SMs ciphertexts — the throughput configuration;
+    //  * pbs_wide_kernel, 1 ciphertext per CTA with the levels transformed in parallel: 3.9 ms per wave of SMs ciphertexts
+    //    — the latency configuration for small batches (one AES block = 128 ciphertexts).
+    const long waves3 = ((nct + 2) / 3 + k.sm_count - 1) / k.sm_count, waves1 = (nct + k.sm_count - 1) / k.sm_count;
+    if (L >= 2 && waves1 * 39 <= waves3 * 86) return launch_pbs_wide<(L >= 2 ? L : 2), 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    return launch_pbs<L, 3, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation
 #endif

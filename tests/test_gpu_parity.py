@@ -109,6 +109,18 @@ def test_pbs_phase_and_noise(gpu64, oracle64):
     assert np.abs(e_gpu - e_ref).max() < 2.0**42
 
 
+def test_pbs_batch_size_independent(gpu64, oracle64):
+    """The throughput kernel (3 ciphertexts per CTA) and the level-parallel small-batch kernel run the same arithmetic in
+    the same order: a ciphertext bootstraps to the SAME words whatever batch it travels in."""
+    ck, ctx = gpu64
+    rng = np.random.default_rng(77)
+    small = oracle64.keyswitch(ck.encrypt_bits(rng.integers(0, 2, 12)))
+    big_batch = np.concatenate([small, rng.integers(0, 2**64, (600 - 12, small.shape[1]), dtype=np.uint64)])
+    alone = ctx.stage_pbs(small)                 # 12 ciphertexts: pbs_wide_kernel
+    together = ctx.stage_pbs(big_batch)[:12]     # 600 ciphertexts: pbs_kernel, B = 3 (wave-count cost model)
+    assert np.array_equal(alone, together)
+
+
 def test_vertical_packing_from_oracle_ggsws(gpu64, oracle64, ol):
     ck, ctx = gpu64
     f = sbox_gal_mul_fn(ol)

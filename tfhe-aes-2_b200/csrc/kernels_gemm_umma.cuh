@@ -6,19 +6,24 @@
 //
 // Exactness: both operands are split into unsigned byte limbs, d' = a0 + 2^8·a1 (d' ∈ [0, 2^16); the lone value 2^16 is
 // patched by pfks_fixup_kernel) and key = Σ_{b<8} 2^(8b)·key_b.  Only limb pairs of weight w = a + b < 8 matter mod 2^64:
-// 15 u8×u8→s32 MMAs per k-block, accumulated BY WEIGHT into 8 tensor-memory accumulators (each partial sum stays below
+// 15 u8×u8→s32 limb products per k-block, accumulated BY WEIGHT into 8 tensor-memory accumulators (each partial sum stays below
 // 2·4128·255² < 2^31), recombined with shifts in the epilogue.
 //
 // One CTA = 128 ciphertexts × 64 columns: 8 weights × 64 columns = all 512 TMEM columns.  Roles (6 warps):
 //   warp 0  lane 0: producer — one cp.async.bulk per operand tile and k-block into a ring of stages, completion on full[s]
-//   warp 1  lane 0: MMA issuer — waits full[s], issues the 15 (8 with one digit limb) tcgen05.mma of the k-block,
+//   warp 1  lane 0: MMA issuer — waits full[s], issues the 4 (2 with one digit limb) tcgen05.mma of the k-block,
 //                   tcgen05.commit → empty[s]; after the last k-block commit → accum
 //   warps 2-5: epilogue — tcgen05.ld the 8 weight accumulators of their 32 TMEM lanes, recombine, subtract from corr, store
 //
 // Operand tiles are prepared in global memory in exactly the shared-memory image the MMA descriptors expect (K-major, no
 // swizzle: 8-row × 16-byte core matrices, 128 B each), so one contiguous bulk copy per tile suffices — no tensor maps:
 //   A tiles  [m tile][kb][limb][k half][row 128][16 B]              (NLIMB·4 KB per k-block; core-matrix strides: K 2048 B, M 128 B)
-//   B tiles  [key j][n tile][kb][byte b 8][k half][col 64][16 B]    (16 KB per k-block;      core-matrix strides: K 1024 B, N 128 B)
+//   B tiles  [key j][n tile][kb][k half][byte b 8][col 64][16 B]    (16 KB per k-block;      core-matrix strides: K 8192 B, N 128 B)
+// With the byte planes adjacent along N, ONE MMA of N = 256 multiplies a digit limb with four consecutive planes and adds
+// into four consecutive weight accumulators (the accumulator of weight w occupies TMEM columns 64·w … 64·w+63): limb 0 ×
+// planes 0-3 → weights 0-3, × planes 4-7 → weights 4-7; limb 1 × planes 0-3 → weights 1-4, × planes 4-6 → weights 5-7 (N = 192).
+// Four MMAs per k-block instead of fifteen of N = 64 — same tensor-core cycles, a quarter of the issue work of the one
+// issuing thread (with fifteen the tensor pipe was only 41 % active).
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
@@ -100,7 +105,7 @@ __global__ void umma_key_tiles_kernel(const uint64_t* __restrict__ key, int nkey
         uint8_t* base = KP + (((size_t)j * ntiles + tile) * nkb + kb) * (size_t)UG_B_BYTES;
 #pragma unroll
         for (int bb = 0; bb < 8; bb++)
-            *reinterpret_cast<uint4*>(base + (((size_t)bb * 2 + khalf) * UG_NT + n) * 16) = make_uint4(pl[bb][0], pl[bb][1], pl[bb][2], pl[bb][3]);
+            *reinterpret_cast<uint4*>(base + (((size_t)khalf * 8 + bb) * UG_NT + n) * 16) = make_uint4(pl[bb][0], pl[bb][1], pl[bb][2], pl[bb][3]);
     }
 }
 
@@ -206,25 +211,23 @@ lwe_gemm_umma_kernel(const uint8_t* __restrict__ DA, int nct, int mtiles, const 
         }
     } else if (warp == 1) {
         if (lane == 0) {
-            constexpr uint32_t idesc = ug::idesc_u8(UG_MT, UG_NT);
+            constexpr uint32_t idesc256 = ug::idesc_u8(UG_MT, 4 * UG_NT), idesc192 = ug::idesc_u8(UG_MT, 3 * UG_NT);
+            constexpr uint32_t B_LBO = 8 * UG_NT * 16, PLANE = UG_NT * 16;           // K-adjacent core matrices, one byte plane
             for (int kb = 0; kb < nkb; kb++) {
                 const int s = kb % Cfg::STAGES;
                 ug::mbar_wait(full_bar(s), (kb / Cfg::STAGES) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a0 = base + s * Cfg::STAGE_BYTES, b0 = a0 + Cfg::A_BYTES;
-#pragma unroll
-                for (int bb = 0; bb < 8; bb++) {
-                    const uint64_t db = ug::smem_desc(b0 + bb * (2 * UG_NT * 16), UG_NT * 16, 128);
-#pragma unroll
-                    for (int limb = 0; limb < NLIMB; limb++) {
-                        const int w = bb + limb;
-                        if (w >= 8) continue;
-                        const uint64_t da = ug::smem_desc(a0 + limb * (2 * UG_MT * 16), UG_MT * 16, 128);
-                        // In issue order the first contribution to weight w is (byte 0, limb 0) for w = 0 and, with two
-                        // limbs, (byte w-1, limb 1) for w >= 1 (with one limb: (byte w, limb 0)): that MMA of k-block 0 overwrites.
-                        const bool first = (kb == 0) && (NLIMB == 1 || limb == 1 || bb == 0);
-                        ug::mma_i8(tmem_base + (uint32_t)(w * UG_NT), da, db, idesc, first ? 0u : 1u);
-                    }
+                const uint64_t da0 = ug::smem_desc(a0, UG_MT * 16, 128);
+                const uint64_t db_lo = ug::smem_desc(b0, B_LBO, 128), db_hi = ug::smem_desc(b0 + 4 * PLANE, B_LBO, 128);
+                // limb 0: planes 0-3 → weights 0-3, planes 4-7 → weights 4-7; in k-block 0 these two overwrite all 512 columns
+                ug::mma_i8(tmem_base, da0, db_lo, idesc256, kb > 0 ? 1u : 0u);
+                ug::mma_i8(tmem_base + 4 * UG_NT, da0, db_hi, idesc256, kb > 0 ? 1u : 0u);
+                if (NLIMB == 2) {
+                    // limb 1 (weight + 1): planes 0-3 → weights 1-4, planes 4-6 → weights 5-7
+                    const uint64_t da1 = ug::smem_desc(a0 + 2 * UG_MT * 16, UG_MT * 16, 128);
+                    ug::mma_i8(tmem_base + UG_NT, da1, db_lo, idesc256, 1u);
+                    ug::mma_i8(tmem_base + 5 * UG_NT, da1, db_hi, idesc192, 1u);
                 }
                 ug::mma_commit(empty_bar(s));                      // frees the stage when these MMAs have read it
             }

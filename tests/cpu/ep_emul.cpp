@@ -32,7 +32,8 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     // threads before the next pass starts
     auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < C::JOBS) fn(t, job); } };
     groups([&](int t, int job) {
-        grp_decomp_fwd1<C>(t, job, [&](int j) { return rot_diff<N>(acc + (size_t)job * N, j, rot[job / C::G]); }, dc, dig.data(), wT.data(), S.data());
+        grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(acc + (size_t)job * N, jj, rot[job / C::G], x0, x1); }, dc, dig.data(),
+                           wT.data(), S.data());
     });
     groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
     for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, L, gf.data(), regs[tid].g);

@@ -355,4 +355,20 @@ TAC_HD uint64_t rot_diff(const uint64_t* __restrict__ p, int j, int rot) {
     return ((v ^ (0ull - neg)) + neg) - p[j];
 }
 
+// both coefficients jj and jj + N/2 of (p · X^rot − p) with the index arithmetic shared: adding N/2 to the rotated index
+// flips bit log2(N)-1 and, when that bit was set, the sign
+template <int N>
+TAC_HD void rot_diff_pair(const uint64_t* __restrict__ p, int jj, int rot, uint64_t& x0, uint64_t& x1) {
+    constexpr int LOGN = (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : (N == 2048) ? 11 : -1;
+    static_assert(LOGN > 0, "unsupported polynomial size");
+    const uint32_t s0 = (uint32_t)(jj - rot) & (uint32_t)(2 * N - 1);
+    const uint32_t i0 = s0 & (uint32_t)(N - 1), i1 = i0 ^ (uint32_t)(N / 2);
+    const uint32_t n0 = s0 >> LOGN, n1 = n0 ^ (i0 >> (LOGN - 1));
+    const uint64_t v0 = p[i0], v1 = p[i1];
+    const uint32_t m0 = 0u - n0, m1 = 0u - n1;
+    const uint64_t w0 = ((uint64_t)((uint32_t)(v0 >> 32) ^ m0) << 32) | ((uint32_t)v0 ^ m0);
+    const uint64_t w1 = ((uint64_t)((uint32_t)(v1 >> 32) ^ m1) << 32) | ((uint32_t)v1 ^ m1);
+    x0 = (w0 + n0) - p[jj];
+    x1 = (w1 + n1) - p[jj + N / 2];
+}
 }  // namespace tac

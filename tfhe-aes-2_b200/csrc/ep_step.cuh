@@ -66,14 +66,14 @@ struct MacCfg {
     static constexpr int SPT = C::M / NT_MAC;
 };
 
-// group phase 1 of a step: decompose the operand polynomial `job` (coef(j) = its coefficient j), keep the digits of
-// levels 1..L-1 in dig, and run forward-FFT pass 1 on the level-L digits straight from registers.
+// group phase 1 of a step: decompose the operand polynomial `job` (coef(jj, x0, x1) yields its coefficients jj and jj + M),
+// keep the digits of levels 1..L-1 in dig, and run forward-FFT pass 1 on the level-L digits straight from registers.
 template <class C, class CoefFn>
 TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
                             cplx* __restrict__ S) {
     uint32_t* dj = dig + (size_t)job * (C::L - 1) * C::M;
     struct Pair { uint64_t x0, x1; };
-    fft_fwd_pass1_2ph<C::N>(t, [&](int jj) { Pair p; p.x0 = coef(jj); p.x1 = coef(jj + C::M); return p; },
+    fft_fwd_pass1_2ph<C::N>(t, [&](int jj) { Pair p; coef(jj, p.x0, p.x1); return p; },
         [&](int jj, const Pair& p, double& a, double& b) {
             uint32_t w[C::L];
             decompose_pair<C::L>(p.x0, p.x1, dc, w);

@@ -45,7 +45,8 @@ struct EpSmem {
     static constexpr size_t bytes = C::acc_words * 8 + C::s_cplx * 16 + C::dig_words * 4 + (size_t)C::M * 16;
 };
 
-// one step on the operand coef(job, j); the accumulators receive  acc += GGSW ⊡ operand.
+// one step on the operand whose coefficients jj and jj + N/2 of polynomial `job` are given by coef(job, jj, x0, x1); the
+// accumulators receive  acc += GGSW ⊡ operand.
 // Ends with a __syncwarp(): the accumulator rows of a job are only touched by the job's own 16-thread group, so the next
 // step's decomposition may follow without a CTA barrier.  (Readers of acc from other groups must __syncthreads() first.)
 // TAC_EP_DBG (development only, tools/pbs_bench.cu): bit 0 skips the Fourier MAC, bit 1 the forward FFT passes, bit 2 the
@@ -76,11 +77,13 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
 #ifdef TAC_EP_TIMING
     long long tac_tprev = clock64();
 #endif
-    if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int j) { return coef(job, j); }, dc, sm.dig, sm.wT, sm.S);
+    if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { coef(job, jj, x0, x1); }, dc, sm.dig, sm.wT, sm.S);
     if (active && !DO_FWD && DO_DEC) {          // decomposition alone
         for (int m = 0; m < C::M / 16; m++) {
             uint32_t w[C::L];
-            decompose_pair<C::L>(coef(job, t + 16 * m), coef(job, t + 16 * m + C::M), dc, w);
+            uint64_t x0, x1;
+            coef(job, t + 16 * m, x0, x1);
+            decompose_pair<C::L>(x0, x1, dc, w);
 #pragma unroll
             for (int s2 = 0; s2 + 1 < C::L; s2++) sm.dig[((size_t)job * (C::L - 1) + s2) * C::M + t + 16 * m] = w[s2];
             sm.S[(size_t)job * C::M + t + 16 * m].x = (double)w[C::L - 1];
@@ -181,7 +184,8 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
         const int* rot = rot_sm + (i & 1) * B;
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
         ep_step_device<C, NT, MAC_DEPTH>(tid, sm, bsk + ggsw_sz * i,
-                              [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot[job / C::G]); }, base_log, out);
+                              [&](int job, int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(sm.acc + (size_t)job * N, jj, rot[job / C::G], x0, x1); },
+                              base_log, out);
     }
     __syncthreads();
     constexpr int LW = K * N + 1;
@@ -263,7 +267,9 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
             for (int m = m0; m < m1; m++) {
                 const int jj = t + 16 * m;
                 uint32_t w[L];
-                decompose_pair<L>(rot_diff<N>(poly, jj, r), rot_diff<N>(poly, jj + C::M, r), dc, w);
+                uint64_t x0, x1;
+                rot_diff_pair<N>(poly, jj, r, x0, x1);
+                decompose_pair<L>(x0, x1, dc, w);
 #pragma unroll
                 for (int s = 0; s < L; s++) dj[(size_t)s * C::M + jj] = w[s];
             }
@@ -367,7 +373,7 @@ vp_kernel(const cplx* __restrict__ ggsw_f, int n_in, int first_ggsw, const uint6
     for (int g = n_in - 1; g >= first_ggsw; g--) {
         const int rot = 2 * N - deg;            // multiply by X^{-deg}
         ep_step_device<C, NT>(tid, sm, gbox + (size_t)g * ggsw_sz,
-                              [&](int job, int j) { return rot_diff<N>(sm.acc + (size_t)job * N, j, rot); }, base_log, outr);
+                              [&](int job, int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(sm.acc + (size_t)job * N, jj, rot, x0, x1); }, base_log, outr);
         deg <<= 1;
     }
     __syncthreads();
@@ -417,7 +423,8 @@ cmux_tree_kernel(const cplx* __restrict__ ggsw_f, int n_in, int ggsw_idx, const 
         for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
     const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
     const cplx* ggsw = ggsw_f + ((size_t)box * n_in + ggsw_idx) * ggsw_sz;
-    ep_step_device<C, NT>(tid, sm, ggsw, [&](int job, int j) { return diff[(size_t)job * N + j]; }, base_log, outr);
+    ep_step_device<C, NT>(tid, sm, ggsw, [&](int job, int jj, uint64_t& x0, uint64_t& x1) { x0 = diff[(size_t)job * N + jj]; x1 = diff[(size_t)job * N + jj + N / 2]; },
+                          base_log, outr);
     __syncthreads();
     uint64_t* dst = node_out + (((size_t)box * n_out + o) * n_pairs + pair) * C::G * N;
     for (int idx = tid; idx < C::G * N; idx += NT) dst[idx] = sm.acc[idx];

@@ -113,7 +113,7 @@ cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__
 #pragma unroll
         for (int c = 0; c < C::G; c++) outr[a][0][c] = mk(0.0, 0.0);
     const int r = rot[blockIdx.x];
-    ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int job, int j) { return rot_diff<SN>(sm.acc + (size_t)job * SN, j, r); }, base_log, outr);
+    ep_step_device<C, NT>(tid, sm, ggsw_f, [&](int job, int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<SN>(sm.acc + (size_t)job * SN, jj, r, x0, x1); }, base_log, outr);
     __syncthreads();
     for (int i = tid; i < C::G * SN; i += NT) g[i] = sm.acc[i];
 }

@@ -25,7 +25,7 @@ __global__ void __launch_bounds__(NT) lat_kernel(const cplx* g_wT, int reps, lon
     long long tsum[6] = {0, 0, 0, 0, 0, 0};
     for (int r = 0; r < reps; r++) {
         long long t0 = clock64();
-        grp_decomp_fwd1<EpCfg<512, 4, 3, 1>>(t, 0, [&](int j) { return rot_diff<N>(ag, j, (r * 37 + 5) & 1023); }, dc, dg - 0, wT, Sg);
+        grp_decomp_fwd1<EpCfg<512, 4, 3, 1>>(t, 0, [&](int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(ag, jj, (r * 37 + 5) & 1023, x0, x1); }, dc, dg - 0, wT, Sg);
         __syncwarp();
         long long t1 = clock64();
         fft_fwd_pass2<N>(t, Sg);

@@ -192,6 +192,19 @@ def pbs_traffic(n_ct):
         return None
 
 
+def tensor_roofline(n_ct, pfks_ms):
+    ops = 2.0 * 15 * 4098 * 12800 * n_ct
+    achieved = ops / (pfks_ms * 1e-3) / 1e12 if pfks_ms > 0 else None
+    peak, src = 4500.0, "nominal dense int8 (MEASURED_PEAKS.json absent)"
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        peak, src = 2.0 * float(mp["bf16_tflops"]), "2 x measured dense bf16 (MEASURED_PEAKS.json bf16_tflops)"
+    except Exception:
+        pass
+    return {"bound": "tensor", "kernel": "umma_digit_tiles_kernel + lwe_gemm_umma_kernel<2> + pfks_fixup_kernel", "achieved": achieved, "peak": peak, "unit": "TOP/s (u8)",
+            "frac": achieved / peak if achieved else None, "peak_source": src, "avg_stage_ms": pfks_ms}
+
+
 def workload_config(args, cpu=False):
     return {"workload": f"AES-128 CTR stream, {args.blocks} counter blocks per GPU x 10 rounds (per-GPU shard of BASELINE config 5: 1024 blocks / 8 GPUs), "
                         "params_sqrd_lvl_64, key schedule precomputed", "blocks_per_gpu": args.blocks, "rounds": 10,
@@ -351,6 +364,10 @@ def run_gpu(args):
                          "peak_source": "DFMA microbenchmark in this run (FP64 is not in MEASURED_PEAKS.json; nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2)",
                          "algorithmic_flop_per_launch": n_ct_per_launch * FLOP_PER_PBS, "avg_launch_ms": pbs_ms, "launches": int(pbs_launches),
                          "whole_step_frac": value / world * FLOP_PER_BLOCK / 1e12 / fp64_peak if fp64_peak else None},
+            # secondary: the PFKS stage (digit tiles + tcgen05 kind::i8 GEMM + fix-up) against the tensor roofline.  Algorithmic
+            # work: 787 M u8 multiply-accumulates per ciphertext (15 byte-limb products × 4098 digits × 12800 columns); peak: twice the
+            # measured dense bf16 throughput of MEASURED_PEAKS.json (int8 runs at 2× bf16 on the B200 tensor cores; nominal 4500 TOP/s).
+            "roofline_tensor": tensor_roofline(n_ct_per_launch, stages["pfks"] / pbs_launches),
             "stage_share": stage_share,
             "cpu_baseline": cpu,
             "latency_s_per_block": None if lat_ms is None else lat_ms * 1e-3,

@@ -19,7 +19,10 @@
  *     PFPKSK           = [j = 0..k][i = 0..kN (last = body)][s (level s+1)][(k+1)N] (pfks_level, pfks_base_log)
  *     LUT              = [n_out][N << max(0, n_in − log2 N)]     (reference WopbsLUTBase)
  *     AES block        = [16 bytes][8 bits, MSB first][kN+1];  key schedule = [44 words][4 bytes][8 bits][kN+1]
- *   - thread safety: a tac_ctx may be used from one thread at a time (one context per GPU / per stream).
+ *   - thread safety: every entry point may be called concurrently from any number of host threads on the same tac_ctx
+ *     (the reference calls circuit_bootstrap from rayon workers: fhe_sbox_gal_mul_pbs.rs:33-41, main.rs:148-152).  Calls on
+ *     one context are serialised by an internal lock; tac_wopbs_coalesced additionally merges concurrent callers into
+ *     one batched GPU pass.  tac_last_error() reports the last error of the CALLING thread.
  */
 #ifndef TFHE_AES_CUDA_H
 #define TFHE_AES_CUDA_H
@@ -68,8 +71,14 @@ int tac_generate_lut(int n_in, int n_out, int polynomial_size, const uint64_t* f
 
 /* ------------------------------------------------------------------ client side (host CPU, like the reference's) */
 /* FheContext::generate_keys_with_params — shortint_woppbs_1bit.rs:245-268 (secret keys only; evaluation keys below).
- * The reference seeds from the OS (engine.rs:164-168); here one u64 seed drives a ChaCha20 stream per object. */
+ * tac_client_keygen_os seeds a 256-bit ChaCha20 master key from the OS (getrandom), like the reference (engine.rs:164-168):
+ * use it for anything but tests.  tac_client_keygen(p, seed) derives the master key from a 64-bit seed — reproducible,
+ * therefore NOT secret: tests and benchmarks only.  Every object (one GLWE / LWE ciphertext) draws from its own stream. */
+tac_client_key* tac_client_keygen_os(const tac_params* p);                    /* NULL if the OS entropy source fails */
 tac_client_key* tac_client_keygen(const tac_params* p, uint64_t seed);
+/* A client around existing secret keys (e.g. loaded with tac_keyfile_*; words must be 0/1); encryption randomness of
+ * this instance comes from fresh OS entropy, so masks are never reused across instances. */
+tac_client_key* tac_client_from_secret_keys(const tac_params* p, const uint64_t* sk_glwe, const uint64_t* sk_lwe);
 void tac_client_free(tac_client_key* ck);
 /* which: 0 sk_glwe (kN words, 0/1), 1 sk_lwe (n), 2 BSK standard, 3 KSK, 4 PFPKSK.  Lengths in words. */
 size_t tac_key_len(const tac_params* p, int which);
@@ -106,6 +115,13 @@ int tac_lut_register(tac_ctx* ctx, int n_in, int n_out, const uint64_t* table, s
  * circuit_bootstrapping_vertical_packing :326-328 = PBS + PFKS + GGSW FFT + vertical packing.) */
 int tac_wopbs_batch(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host, uint64_t* out_host);
 int tac_wopbs_batch_dev(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_dev, uint64_t* out_dev);
+/* The same operator for callers that arrive one circuit_bootstrap at a time from many threads — the shape of the
+ * reference's rayon fan-out (16 bytes × blocks, fhe_sbox_gal_mul_pbs.rs:33-41): blocks until this request is done;
+ * requests that arrive within `window_us` of each other (and while a pass is running) are merged into one batched pass
+ * per LUT.  Defaults: window 200 µs, at most 4096 requests per pass. */
+int tac_wopbs_coalesced(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host, uint64_t* out_host);
+int tac_ctx_set_coalescing(tac_ctx* ctx, int window_us, int max_batch);
+int tac_ctx_coalescing_stats(tac_ctx* ctx, uint64_t* requests, uint64_t* passes);   /* since creation */
 /* BitXorAssign for BitCt — shortint_woppbs_1bit.rs:134-142 (lwe_ciphertext_add_assign); noise bookkeeping stays with the caller */
 int tac_lwe_add_batch(tac_ctx* ctx, uint64_t* a_host, const uint64_t* b_host, size_t n_cts);
 int tac_lwe_add_batch_dev(tac_ctx* ctx, uint64_t* a_dev, const uint64_t* b_dev, size_t n_cts);
@@ -135,6 +151,13 @@ int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64
  * acc: [n_acc][(k+1)N] in/out, rot[n_acc] in [0, 2N).  Exercises the FFT / external-product core alone. */
 int tac_stage_cmux_rotate(tac_ctx* ctx, int levels, int base_log, const uint64_t* ggsw_std_host, int n_acc, const int32_t* rot,
                           uint64_t* acc_host);
+/* [U] FourierGgswCiphertext::fill_with_forward_fourier on its own: n_polys torus polynomials [n_polys][N] → Fourier slots
+ * [n_polys][N/2] (re, im) doubles, values scaled by 2^-64 · 2/N, in the slot order tac_fft_slot_frequencies reports
+ * (slot s holds frequency freq[s] of the size-N/2 FFT of the folded, twisted polynomial). */
+int tac_stage_poly_fft(tac_ctx* ctx, size_t n_polys, const uint64_t* polys_host, double* out_host);
+int tac_fft_slot_frequencies(int polynomial_size, int32_t* freq /* [N/2] */);
+/* [U] extract_lwe_sample_from_glwe_ciphertext(.., MonomialDegree(0)): [n_glwe][(k+1)N] → [n_glwe][kN+1] */
+int tac_stage_sample_extract(tac_ctx* ctx, size_t n_glwe, const uint64_t* glwe_host, uint64_t* out_host);
 /* Per-stage device time.  With profiling on, every pipeline pass records CUDA events on the context's stream (no host
  * synchronisation); tac_ctx_stage_times synchronises, returns the summed milliseconds since the previous call —
  * [0] keyswitch [1] PBS [2] PFKS [3] GGSW FFT [4] vertical packing — and the number of passes, then resets. */

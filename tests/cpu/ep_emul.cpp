@@ -13,13 +13,13 @@ template <int N, int K, int L, int B, int NT>
 static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
     typedef EpCfg<N, K, L, B> C;
     typedef MacCfg<C, NT> MC;
-    std::vector<cplx> wT(C::M); build_wT(N, wT.data());
+    std::vector<cplx> wT(tab_len(N)); build_wT(N, wT.data());
     // Fourier GGSW with the kernels' own key transform
     const int polys = L * C::G * C::G;
     std::vector<cplx> gf((size_t)polys * C::M), kbuf(C::M);
     for (int q = 0; q < polys; q++) {
-        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, wT.data(), kbuf.data());
-        for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, kbuf.data());
+        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / C::M, kbuf.data());
+        for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, wT.data(), kbuf.data());
         for (int s = 0; s < C::M; s++) gf[(size_t)q * C::M + s] = kbuf[s];
     }
     struct Regs { cplx v[MC::SPT][C::B][C::G]; cplx g[MAC_DEPTH][C::G]; };
@@ -33,14 +33,14 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < C::JOBS) fn(t, job); } };
     groups([&](int t, int job) {
         grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(acc + (size_t)job * N, jj, rot[job / C::G], x0, x1); }, dc, dig.data(),
-                           wT.data(), S.data());
+                           S.data());
     });
-    groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
+    groups([&](int t, int job) { grp_fwd2<C>(t, job, wT.data(), S.data()); });
     for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, L, gf.data(), regs[tid].g);
     for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, L, gf.data(), S.data(), regs[tid].v, regs[tid].g);
     for (int lev = L - 1; lev >= 1; lev--) {
-        groups([&](int t, int job) { grp_fwd1<C>(t, job, lev, dc, dig.data(), wT.data(), S.data()); });
-        groups([&](int t, int job) { grp_fwd2<C>(t, job, S.data()); });
+        groups([&](int t, int job) { grp_fwd1<C>(t, job, lev, dc, dig.data(), S.data()); });
+        groups([&](int t, int job) { grp_fwd2<C>(t, job, wT.data(), S.data()); });
         for (int tid = 0; tid < NT; tid++) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, gf.data(), regs[tid].g);
         for (int tid = 0; tid < NT; tid++) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, gf.data(), S.data(), regs[tid].v, regs[tid].g);
     }
@@ -53,11 +53,11 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
 template <int N>
 static void emul_fft(const double* in, double* out_re, double* out_im, int* slot_freq) {
     const int M = N / 2, P = M / 16;
-    std::vector<cplx> wT(M), S(M); build_wT(N, wT.data());
-    for (int t = 0; t < 16; t++) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { a = in[jj]; b = in[jj + M]; }, wT.data(), S.data());
-    for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, S.data());
+    std::vector<cplx> wT(tab_len(N)), S(M); build_wT(N, wT.data());
+    for (int t = 0; t < 16; t++) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { a = in[jj]; b = in[jj + M]; }, S.data());
+    for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, wT.data(), S.data());
     for (int s = 0; s < M; s++) { out_re[s] = S[s].x; out_im[s] = S[s].y; }
-    for (int q = 0; q < P; q++) for (int i = 0; i < 16; i++) slot_freq[slot_of(q, i)] = q + P * bitrev<16>(i);
+    for (int q = 0; q < P; q++) for (int i = 0; i < 16; i++) slot_freq[slot_of(q, i)] = q + P * i;
     // inverse back into `in`-shaped output appended after the spectrum (roundtrip check): out_re[M..M+N)
     for (int t = 0; t < 16; t++) fft_inv_passA<N>(t, wT.data(), S.data());
     for (int t = 0; t < 16; t++) fft_inv_passB<N>(t, S.data(), [&](int jj, double re, double im) { out_re[M + jj] = re / M; out_re[M + jj + M] = im / M; });

@@ -67,6 +67,51 @@ def test_client_encrypt_decrypt_equal_oracle(ck64, oracle64):
     assert ck64.encrypt_bits([]).shape == (0, ck64.params.big_lwe_size)
 
 
+def test_client_default_seed_is_os_entropy(tac):
+    """a default ClientKey must not be derivable from a public constant (the reference seeds from the OS,
+    engine.rs:164-168); an explicit seed stays reproducible for tests"""
+    a, b, z = tac.ClientKey(64), tac.ClientKey(64), tac.ClientKey(64, seed=0)
+    assert a.seed is None
+    assert not np.array_equal(a.sk_glwe, b.sk_glwe) and not np.array_equal(a.sk_glwe, z.sk_glwe)
+    assert np.array_equal(z.sk_glwe, tac.ClientKey(64, seed=0).sk_glwe)
+    bits = [1, 0, 1, 1]
+    ca, cb = a.encrypt_bits(bits, first_index=0), a.encrypt_bits(bits, first_index=0)
+    assert a.decrypt_bits(ca).tolist() == bits
+    assert np.array_equal(ca, cb)                                   # same instance, same index: same stream (documented)
+    # a client rebuilt around the same secret keys draws fresh masks: index 0 of the new instance is not a reuse
+    a2 = tac.ClientKey(64, secret_keys=(a.sk_glwe, a.sk_lwe))
+    c2 = a2.encrypt_bits(bits, first_index=0)
+    assert not np.array_equal(c2[:, :8], ca[:, :8])
+    assert a.decrypt_bits(c2).tolist() == bits and a2.decrypt_bits(ca).tolist() == bits
+    with pytest.raises(RuntimeError):
+        tac.ClientKey(64, secret_keys=(a.sk_glwe + np.uint64(2), a.sk_lwe))
+    # key views keep their owner alive
+    k = tac.ClientKey(64, seed=5).sk_lwe
+    import gc; gc.collect()
+    assert set(np.unique(k)) <= {0, 1} and k.size == 677
+
+
+def test_context_rejects_unsupported_parameter_sets(tac):
+    """constraints the kernels assume beyond (N, k) are validated up front (before any device is touched)"""
+    import ctypes as C
+    L = tac.load_library()
+    def err_for(**kw):
+        p = tac.params_preset(64)
+        for k, v in kw.items():
+            setattr(p, k, v)
+        h = L.tac_ctx_create(C.byref(p), 0)
+        if h:
+            L.tac_ctx_destroy(h)
+            return None
+        return L.tac_last_error(None).decode()
+    assert "base_log must be <= 7" in err_for(ks_base_log=8)
+    assert "must be odd" in err_for(lwe_dimension=676)
+    assert "16-bit fields" in err_for(pbs_base_log=16)
+    assert "cbs_level" in err_for(cbs_level=2)
+    assert "below 16000" in err_for(ks_level=8, ks_base_log=2)
+    assert "unsupported (polynomial_size" in err_for(polynomial_size=2048)
+
+
 def test_client_other_parameter_sets(tac, ol):
     ck = tac.ClientKey(4, seed=3)
     assert ck.decrypt_bits(ck.encrypt_bits([1, 0, 1])).tolist() == [1, 0, 1]

@@ -54,6 +54,56 @@ def test_pfks_bit_exact(gpu64, oracle64, n):
     assert np.array_equal(got, oracle64.pfks(x))
 
 
+def test_pfks_tie_list_overflow_is_exact(gpu64, oracle64):
+    """More +B/2 tie digits than the fix-up list holds (65536): every element 2^47 decomposes to the level-2 digit +2^15, so
+    33 ciphertexts carry 33·2049 = 67617 of them.  The scan fallback must still give the oracle's words (it used to drop
+    the excess silently)."""
+    ck, ctx = gpu64
+    x = np.full((33, ck.params.big_lwe_size), 1 << 47, dtype=np.uint64)
+    x[1, ::3] = np.uint64(1 << 63)                                   # level-1 ties as well
+    x[2, 5:900] = np.uint64(12345678901234567)                       # and ordinary elements in between
+    assert np.array_equal(ctx.stage_pfks(x), oracle64.pfks(x))
+    # and a batch just below the capacity still goes through the list path
+    assert np.array_equal(ctx.stage_pfks(x[:3]), oracle64.pfks(x[:3]))
+
+
+def test_sample_extract_bit_exact(gpu64):
+    """[U] extract_lwe_sample_from_glwe_ciphertext(.., MonomialDegree(0)): body = b[0]; mask_i[0] = a_i[0], mask_i[j] = −a_i[N−j]"""
+    ck, ctx = gpu64
+    p = ck.params
+    k, N = p.glwe_dimension, p.polynomial_size
+    rng = np.random.default_rng(15)
+    g = rng.integers(0, 2**64, (7, k + 1, N), dtype=np.uint64)
+    got = ctx.stage_sample_extract(g)
+    want = np.empty((7, k * N + 1), dtype=np.uint64)
+    for i in range(k):
+        want[:, i * N] = g[:, i, 0]
+        want[:, i * N + 1:(i + 1) * N] = (np.uint64(0) - g[:, i, :0:-1])
+    want[:, k * N] = g[:, k, 0]
+    assert np.array_equal(got, want)
+    assert ctx.stage_sample_extract(g[:0]).shape == (0, k * N + 1)
+
+
+def test_poly_fft_matches_numpy(gpu64):
+    """fill_with_forward_fourier alone ([U] Fft::forward_as_torus): size-N/2 complex FFT of the folded, twisted polynomial
+    (torus words read as signed fractions), compared through the kernel's slot permutation; relative tolerance 2^-40"""
+    ck, ctx = gpu64
+    N = ck.params.polynomial_size
+    M = N // 2
+    rng = np.random.default_rng(16)
+    polys = rng.integers(0, 2**64, (40, N), dtype=np.uint64)
+    polys[0] = 0
+    polys[1] = np.uint64(1 << 63)
+    got = ctx.stage_poly_fft(polys)
+    freq = ctx.fft_slot_frequencies()
+    assert sorted(freq.tolist()) == list(range(M))
+    x = polys.astype(np.int64).astype(np.float64) / 2.0**64
+    z = (x[:, :M] + 1j * x[:, M:]) * np.exp(1j * np.pi * np.arange(M) / N)
+    want = np.fft.fft(z, axis=1)[:, freq] / M                      # the kernels pre-scale by 1/M (the inverse is unnormalised)
+    scale = np.abs(want).max()
+    assert np.abs(got - want).max() < 2.0**-40 * scale, np.log2(np.abs(got - want).max() / scale)
+
+
 def test_lwe_add_batch_bit_exact(gpu64):
     ck, ctx = gpu64
     rng = np.random.default_rng(3)
@@ -147,6 +197,27 @@ def test_vertical_packing_from_oracle_ggsws(gpu64, oracle64, ol):
         assert d.max() < 2.0**57, np.log2(d + 1).round(1).tolist()
 
 
+def test_vertical_packing_tie_free_all_outputs_tight(gpu64, oracle64, ol):
+    """Same stage with a LUT whose CMux operands never sit on a decomposition tie: entries 2^61 (bit 0) and 3·2^61 (bit 1)
+    still decode, and every difference of two entries is 0 or ±2^62 — top digit ±2^11, at least 2^61 away from the ±2^12
+    tie — so both runs take the same digits everywhere and EVERY output must agree to f64 rounding (< 2^42)."""
+    ck, ctx = gpu64
+    tac = __import__("importlib").import_module("tfhe-aes-2_b200")
+    f = sbox_gal_mul_fn(ol)
+    base = ctx.generate_lookup_table(8, 24, f).table
+    table = np.where(base != 0, np.uint64(3 << 61), np.uint64(1 << 61)).astype(np.uint64)
+    table[:, 256:] = 0                                             # entries beyond 2^n_in stay 0 like the reference's
+    lut = tac.LookupTable(table, 8, 24)
+    vals = [0x00, 0x53, 0xA7]
+    ggsw = np.stack([oracle64.pfks(oracle64.pbs(oracle64.keyswitch(ck.encrypt_bytes([v])[0]))) for v in vals])
+    got = ctx.stage_vertical_packing(ggsw, lut)
+    for i, v in enumerate(vals):
+        ref = oracle64.vertical_packing(ggsw[i], 8, table, 24)
+        assert ck.decrypt_bytes(got[i]) == f(v).to_bytes(3, "big") == oracle64.decrypt_bytes(ref)
+        d = np.abs(signed(ck.decrypt_phases(got[i]) - ck.decrypt_phases(ref)))
+        assert d.max() < 2.0**42, np.log2(d + 1).round(1).tolist()
+
+
 # ---------------------------------------------------------------------------------------------- the operator, decrypt-checked
 def test_sbox_gal_mul_all_256_bytes(gpu64, ol):
     """BASELINE config 2: the 8-in/24-out SBOX·{1,2,3} WoP-PBS, all byte values in one batch"""
@@ -179,6 +250,52 @@ def test_wopbs_batch_sizes_match_oracle(gpu64, oracle64, ol, batch):
     if batch <= 2:
         ref = oracle64.circuit_bootstrap(cts, lut.table, 8)
         assert oracle64.decrypt_bytes(ref.reshape(-1, oracle64.big1)) == bytes(ol.sbox(v) for v in vals)
+
+
+def test_concurrent_callers_on_one_context(gpu64, ol):
+    """The reference calls circuit_bootstrap from rayon workers — 16 SBOX bytes at a time (fhe_sbox_gal_mul_pbs.rs:33-41).
+    16 host threads issue single-SBOX calls on ONE context: every result must decrypt correctly, and the coalescing entry
+    point must have merged them into far fewer GPU passes than requests.  Plain tac_wopbs_batch calls are serialised by
+    the context lock and must stay correct too."""
+    import threading
+    ck, ctx = gpu64
+    f = sbox_gal_mul_fn(ol)
+    lut = ctx.generate_lookup_table(8, 24, f)
+    lut8 = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    lut.device_id(ctx); lut8.device_id(ctx)
+    vals = [(37 * i + 11) % 256 for i in range(16)]
+    bits = [[ck.encrypt(b) for b in __import__("importlib").import_module("tfhe-aes-2_b200").u8_to_bits(v)] for v in vals]
+    ctx.set_coalescing(window_us=2000)
+    before = ctx.coalescing_stats()
+    res, errs = [None] * 16, []
+
+    def worker(i):
+        try:
+            which = lut if i % 4 else lut8                         # two LUTs in flight: grouped per LUT inside a pass
+            res[i] = ctx.circuit_bootstrap_coalesced(bits[i], which)
+        except Exception as e:                                     # noqa: BLE001
+            errs.append(e)
+
+    for rounds in range(2):
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(16)]
+        [t.start() for t in th]; [t.join() for t in th]
+        assert not errs, errs
+        for i, v in enumerate(vals):
+            got = bytes(__import__("importlib").import_module("tfhe-aes-2_b200").bits_to_u8([ck.decrypt(b) for b in res[i][8 * j:8 * j + 8]])
+                        for j in range(len(res[i]) // 8))
+            assert got == (f(v).to_bytes(3, "big") if i % 4 else bytes([ol.sbox(v)])), (i, got.hex())
+    after = ctx.coalescing_stats()
+    assert after["requests"] - before["requests"] == 32
+    assert after["passes"] - before["passes"] <= 16, after              # 32 requests, two LUTs: merged, not one pass each
+    # the plain batch entry point from many threads: serialised by the context lock
+    out = [None] * 8
+    def plain(i):
+        out[i] = ctx.circuit_bootstrap_batch(np.stack([b.ct for b in bits[i]])[None], lut8)
+    th = [threading.Thread(target=plain, args=(i,)) for i in range(8)]
+    [t.start() for t in th]; [t.join() for t in th]
+    for i in range(8):
+        assert ck.decrypt_bytes(out[i][0]) == bytes([ol.sbox(vals[i])])
+    ctx.set_coalescing(window_us=200)
 
 
 def test_wopbs_empty_batch(gpu64, ol):
@@ -227,6 +344,27 @@ def test_increment_1bit_adder_with_trivial_carry(gpu64, tac):
             new.append(nb)
         value = list(reversed(new))
         assert sum(ck.decrypt(b) << (3 - i) for i, b in enumerate(value)) == expect
+
+
+def test_increment_8bit_adder_9_to_9(gpu64, tac):
+    """reference test_increment_8bit_adder (:838-877): a 9→9 LUT — n_in = log2 N, nine blind-rotation steps, the first by
+    X^-256 — with a trivial carry-in, rippling through all 16 bytes, three increments of 0x…00FF"""
+    ck, ctx = gpu64
+    add_fn = lambda val: (val & 0xFF) + tac.u16_to_bits(val)[7]
+    lut = ctx.generate_lookup_table(9, 9, add_fn)
+    value_clear = bytes(15) + b"\xff"
+    value = [[ck.encrypt(b) for b in tac.u8_to_bits(v)] for v in value_clear]
+    for _ in range(3):
+        carry = ctx.trivial(1)
+        new = []
+        for byte in reversed(value):
+            out = ctx.circuit_bootstrap([carry] + byte, lut)
+            carry, nb = out[0], out[1:]
+            assert nb[0].noise_level.noise_level_squared == 9
+            new.append(nb)
+        value = list(reversed(new))
+    got = bytes(tac.bits_to_u8([ck.decrypt(b) for b in byte]) for byte in value)
+    assert got == bytes(14) + b"\x01\x02"
 
 
 def test_xor_of_bootstrapped_bits_respects_bookkeeping(gpu64, tac):
@@ -311,6 +449,21 @@ def test_lvl1_cmux_tree_16_to_8(tac):
     tv = ctx.generate_lookup_table(16, 8, xor_fn)
     out = ctx.circuit_bootstrap_batch(ck.encrypt_bytes([b1, b2]).reshape(1, 16, -1), tv)
     assert ck.decrypt_bytes(out[0]) == bytes([b1 ^ b2])
+
+
+def test_lvl1_pfks_integer_gemm_bit_exact(tac, ol):
+    """params_sqrd_lvl_1 has pfks_base_log = 24: digits wider than 16 bits take the 64-bit integer-pipe GEMM
+    (lwe_gemm_kernel) instead of the tcgen05 path — bit-exact against the oracle on the same keys, ties included"""
+    ck = tac.ClientKey(1, seed=SEED + 1).gen_eval_keys()
+    ctx = tac.FheContext(ck.params)
+    ctx.upload_keys(ck)
+    orc = ol.Oracle(1, seed=SEED + 1, raw=(ck.sk_glwe, ck.sk_lwe, ck.bsk, ck.ksk, ck.pfpksk))
+    rng = np.random.default_rng(31)
+    for n in (1, 19, 270):
+        x = rng.integers(0, 2**64, (n, ck.params.big_lwe_size), dtype=np.uint64)
+        x[0, :6] = [0, 2**64 - 1, 1 << 63, (1 << 63) - 1, 1 << 39, (1 << 63) + (1 << 39)]
+        assert np.array_equal(ctx.stage_pfks(x), orc.pfks(x)), n
+    assert np.array_equal(ctx.stage_keyswitch(x[:5]), orc.keyswitch(x[:5]))
 
 
 @pytest.mark.parametrize("pid", [4, 256])

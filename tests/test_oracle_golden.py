@@ -171,6 +171,25 @@ def test_oracle_adder_with_trivial_carry(oracle64, ol):
     assert oracle64.decrypt_bits(out).tolist() == [1, 0]
 
 
+def test_oracle_increment_8bit_adder_9_to_9(oracle64, ol):
+    # reference test_increment_8bit_adder (:838-877), shortened to the two low bytes (the GPU test runs all 16): the 9→9
+    # LUT has n_in = log2 N — nine blind-rotation steps, the first by X^-256 — and a trivial carry-in
+    add = lambda v: (v & 0xFF) + ((v >> 8) & 1)
+    lut = oracle64.generate_lookup_table(9, 9, add)
+    assert lut.shape == (9, 512)
+    value = oracle64.encrypt_bytes([0x00, 0xFF])
+    for _ in range(2):
+        carry = np.zeros(oracle64.big1, dtype=np.uint64)
+        carry[-1] = 1 << 63
+        new = []
+        for byte in value[::-1]:
+            out = oracle64.circuit_bootstrap(np.concatenate([carry[None], byte]), lut, 9)
+            carry, nb = out[0], out[1:]
+            new.append(nb)
+        value = np.stack(new[::-1])
+    assert oracle64.decrypt_bytes(value.reshape(-1, oracle64.big1)) == bytes([0x01, 0x01])
+
+
 def test_oracle_cmux_tree_16_to_8(ol):
     # reference :626-659 — 16 inputs at N = 1024 (params_sqrd_lvl_1) exercises the real CMux tree (6 tree bits)
     o = ol.Oracle(1, seed=77)

@@ -61,6 +61,8 @@ _SIGNATURES = {
     "tac_lut_len": (C.c_size_t, [C.c_int, C.c_int]),
     "tac_generate_lut": (C.c_int, [C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
     "tac_client_keygen": (C.c_void_p, [C.POINTER(Params), C.c_uint64]),
+    "tac_client_keygen_os": (C.c_void_p, [C.POINTER(Params)]),
+    "tac_client_from_secret_keys": (C.c_void_p, [C.POINTER(Params), _u64p, _u64p]),
     "tac_client_free": (None, [C.c_void_p]),
     "tac_key_len": (C.c_size_t, [C.POINTER(Params), C.c_int]),
     "tac_client_gen_eval_keys": (C.c_int, [C.c_void_p, C.c_int]),
@@ -81,6 +83,9 @@ _SIGNATURES = {
     "tac_lut_register": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, C.c_size_t]),
     "tac_wopbs_batch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tac_wopbs_batch_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tac_wopbs_coalesced": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "tac_ctx_set_coalescing": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "tac_ctx_coalescing_stats": (C.c_int, [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "tac_lwe_add_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tac_lwe_add_batch_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "tac_aes_key_schedule": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
@@ -93,6 +98,9 @@ _SIGNATURES = {
     "tac_stage_pfks": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "tac_stage_vertical_packing": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, _u64p]),
     "tac_stage_cmux_rotate": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, C.c_int, _i32p, _u64p]),
+    "tac_stage_poly_fft": (C.c_int, [C.c_void_p, C.c_size_t, _u64p, np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")]),
+    "tac_fft_slot_frequencies": (C.c_int, [C.c_int, _i32p]),
+    "tac_stage_sample_extract": (C.c_int, [C.c_void_p, C.c_size_t, _u64p, _u64p]),
     "tac_ctx_set_profiling": (C.c_int, [C.c_void_p, C.c_int]),
     "tac_ctx_stage_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "tac_bench_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
@@ -176,7 +184,7 @@ class LookupTable:
         self._ids = {}
 
     def device_id(self, ctx):
-        key = id(ctx)
+        key = ctx._token          # unique per FheContext for the life of the process (id() can be reused after garbage collection)
         if key not in self._ids:
             rc = ctx.L.tac_lut_register(ctx.h, self.input_bits, self.output_bits, self.table.reshape(-1), self.table.size)
             if rc < 0:
@@ -185,14 +193,32 @@ class LookupTable:
         return self._ids[key]
 
 
-class ClientKey:
-    """reference ClientKey (shortint_woppbs_1bit.rs:189-226): holds the secret keys, encrypts/decrypts bits on the CPU."""
+class _OwnedArray(np.ndarray):
+    """view of C-owned key memory that keeps its owner (the ClientKey) alive"""
+    _owner = None
 
-    def __init__(self, params, seed=0):
+
+class ClientKey:
+    """reference ClientKey (shortint_woppbs_1bit.rs:189-226): holds the secret keys, encrypts/decrypts bits on the CPU.
+
+    seed=None (default): all key material and encryption randomness derive from 256 bits of OS entropy, like the
+    reference (engine.rs:164-168).  An integer seed gives reproducible — hence publicly computable — keys: tests and
+    benchmarks only.  `secret_keys=(sk_glwe, sk_lwe)` wraps existing keys (see save_keys / load_keys)."""
+
+    def __init__(self, params, seed=None, secret_keys=None):
         self.L = load_library()
         self.params = params if isinstance(params, Params) else params_preset(params)
         self.seed = seed
-        self.h = self.L.tac_client_keygen(C.byref(self.params), seed)
+        if secret_keys is not None:
+            g, l = (np.ascontiguousarray(a, dtype=np.uint64) for a in secret_keys)
+            assert g.size == self.params.big_lwe_dimension and l.size == self.params.lwe_dimension
+            self.h = self.L.tac_client_from_secret_keys(C.byref(self.params), g, l)
+        elif seed is None:
+            self.h = self.L.tac_client_keygen_os(C.byref(self.params))
+        else:
+            self.h = self.L.tac_client_keygen(C.byref(self.params), seed)
+        if not self.h:
+            raise RuntimeError("client key creation failed (OS entropy source unavailable, or secret key words not 0/1)")
         self._next_index = itertools.count()
         self._lock = threading.Lock()
         self._enc_counter = 0
@@ -210,7 +236,9 @@ class ClientKey:
         ptr = self.L.tac_client_key_ptr(self.h, which)
         if not ptr:
             raise RuntimeError("evaluation keys not generated yet (gen_eval_keys)")
-        return np.ctypeslib.as_array(ptr, shape=(self.L.tac_key_len(C.byref(self.params), which),))
+        arr = np.ctypeslib.as_array(ptr, shape=(self.L.tac_key_len(C.byref(self.params), which),)).view(_OwnedArray)
+        arr._owner = self          # the memory belongs to the C object tac_client_free releases in __del__
+        return arr
 
     def gen_eval_keys(self, threads=0):
         rc = self.L.tac_client_gen_eval_keys(self.h, threads)
@@ -346,6 +374,9 @@ class NoiseContext:
         return BitCt.trivial(bit, self)
 
 
+_ctx_tokens = itertools.count(1)
+
+
 class FheContext(NoiseContext):
     """Server-side context — reference FheContext (shortint_woppbs_1bit.rs:166-172): evaluation keys + parameters +
     ciphertext-id counter.  The keys live in HBM of one B200."""
@@ -359,6 +390,7 @@ class FheContext(NoiseContext):
             raise RuntimeError("tac_ctx_create failed: " + (self.L.tac_last_error(None) or b"").decode())
         if stream is not None:
             self._check(self.L.tac_ctx_set_stream(self.h, C.c_void_p(stream)))
+        self._token = next(_ctx_tokens)
         self._ct_counter = itertools.count()
         self._id_lock = threading.Lock()
 
@@ -381,7 +413,7 @@ class FheContext(NoiseContext):
             raise RuntimeError(f"tfhe_aes_cuda error {rc}: {self.last_error()}")
 
     @classmethod
-    def generate_keys(cls, pid, seed=0, device=0, stream=None):
+    def generate_keys(cls, pid, seed=None, device=0, stream=None):
         """generate_keys_sqrd_lvl_{1,4,64,256} (:229-243): returns (ClientKey, FheContext) with the keys uploaded."""
         ck = ClientKey(pid, seed).gen_eval_keys()
         ctx = cls(ck.params, device, stream)
@@ -438,6 +470,24 @@ class FheContext(NoiseContext):
         out = self.circuit_bootstrap_batch(arr, lut)[0]
         level = NOMINAL * len(bits)
         return [BitCt.with_noise_level(out[i].copy(), level, self) for i in range(lut.output_bits)]
+
+    def circuit_bootstrap_coalesced(self, bits, lut):
+        """circuit_bootstrap for callers that arrive from many threads (the reference's rayon pattern): concurrent calls
+        are merged into one batched GPU pass (tac_wopbs_coalesced)."""
+        assert len(bits) == lut.input_bits
+        a = np.ascontiguousarray(np.stack([b.ct for b in bits]), dtype=np.uint64)
+        out = np.empty((lut.output_bits, self.params.big_lwe_size), dtype=np.uint64)
+        self._check(self.L.tac_wopbs_coalesced(self.h, lut.device_id(self), 1, a.ctypes.data, out.ctypes.data))
+        level = NOMINAL * len(bits)
+        return [BitCt.with_noise_level(out[i].copy(), level, self) for i in range(lut.output_bits)]
+
+    def set_coalescing(self, window_us=200, max_batch=4096):
+        self._check(self.L.tac_ctx_set_coalescing(self.h, window_us, max_batch))
+
+    def coalescing_stats(self):
+        r, p = C.c_uint64(), C.c_uint64()
+        self._check(self.L.tac_ctx_coalescing_stats(self.h, C.byref(r), C.byref(p)))
+        return {"requests": r.value, "passes": p.value}
 
     def circuit_bootstrap_batch(self, in_cts, lut):
         """batched raw form: in [batch][n_in][big+1] → out [batch][n_out][big+1] (host arrays)."""
@@ -507,6 +557,26 @@ class FheContext(NoiseContext):
         g = np.ascontiguousarray(ggsw_std, dtype=np.uint64).reshape(-1, lut.input_bits, G, G * N)
         out = np.empty((g.shape[0], lut.output_bits, self.params.big_lwe_size), dtype=np.uint64)
         self._check(self.L.tac_stage_vertical_packing(self.h, lut.device_id(self), g.shape[0], g.reshape(-1), out.reshape(-1)))
+        return out
+
+    def stage_poly_fft(self, polys):
+        """fill_with_forward_fourier of torus polynomials [n][N] → complex [n][N/2] in slot order (see fft_slot_frequencies)"""
+        N = self.params.polynomial_size
+        a = np.ascontiguousarray(polys, dtype=np.uint64).reshape(-1, N)
+        out = np.empty((a.shape[0], N // 2, 2), dtype=np.float64)
+        self._check(self.L.tac_stage_poly_fft(self.h, a.shape[0], a.reshape(-1), out.reshape(-1)))
+        return out[..., 0] + 1j * out[..., 1]
+
+    def fft_slot_frequencies(self):
+        f = np.empty(self.params.polynomial_size // 2, dtype=np.int32)
+        assert self.L.tac_fft_slot_frequencies(self.params.polynomial_size, f) == 0
+        return f
+
+    def stage_sample_extract(self, glwes):
+        G, N = self.params.glwe_dimension + 1, self.params.polynomial_size
+        g = np.ascontiguousarray(glwes, dtype=np.uint64).reshape(-1, G * N)
+        out = np.empty((g.shape[0], self.params.big_lwe_size), dtype=np.uint64)
+        self._check(self.L.tac_stage_sample_extract(self.h, g.shape[0], g.reshape(-1), out.reshape(-1)))
         return out
 
     def stage_cmux_rotate(self, ggsw_std, levels, base_log, acc, rot):

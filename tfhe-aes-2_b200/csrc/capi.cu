@@ -7,9 +7,12 @@
 #include "ep_step.cuh"
 #include "shape_launch.h"
 
+#include <chrono>
 #include <cmath>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -17,7 +20,8 @@ using namespace tac;
 
 namespace {
 
-thread_local std::string g_create_error;
+// last error of the calling thread (entry points may be used from many threads; a per-context string would race)
+thread_local std::string g_error;
 
 struct DevBuf {
     void* p = nullptr;
@@ -32,16 +36,36 @@ struct Lut {
 };
 
 enum Stage { ST_KS = 0, ST_PBS, ST_PFKS, ST_FFT, ST_VP, ST_COUNT };
+constexpr uint32_t kFixCap = 1u << 16;
 
 }  // namespace
 
+// a circuit_bootstrap call waiting in the coalescing queue (tac_wopbs_coalesced)
+struct PendingWopbs {
+    int lut_id, batch;
+    const uint64_t* in;
+    uint64_t* out;
+    int rc = 0;
+    bool done = false;
+    std::string err;
+};
+
 struct tac_ctx {
+    // Every entry point takes `mu` (recursive: entry points call each other), so a context may be shared by any number of
+    // host threads — the reference calls circuit_bootstrap from rayon workers (fhe_sbox_gal_mul_pbs.rs:33-41, main.rs:148-152).
+    std::recursive_mutex mu;
+    // coalescing queue: concurrent single-SBOX callers are merged into one batched pass
+    std::mutex q_mu;
+    std::condition_variable q_cv;
+    std::vector<PendingWopbs*> q_pending;
+    bool q_leader = false;
+    int q_window_us = 200, q_max_batch = 4096;
+    uint64_t q_passes = 0, q_requests = 0;
     TacParams p;
     int device = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    std::string err;
     // keys
     cplx* bsk_f = nullptr;
     uint64_t* ksk = nullptr;
@@ -63,6 +87,7 @@ struct tac_ctx {
     // workspace
     DevBuf ws_in, ws_out, ws_small, ws_ksdig, ws_pbs, ws_pfdig, ws_ggsw, ws_ggswf, ws_tree_a, ws_tree_b, ws_state, ws_muls, ws_misc;
     size_t max_cts = 16384;
+    uint32_t fix_cap = kFixCap;      // capacity of the PFKS tie list in use (TAC_FIX_CAP lowers it: exercises the overflow path)
     // profiling: one event tuple per pipeline pass, recorded without synchronising; read back by tac_ctx_stage_times
     bool profiling = false;
     struct ProfRec { cudaEvent_t ev[ST_COUNT + 1]; };
@@ -79,8 +104,8 @@ struct tac_ctx {
 
 namespace {
 
-int fail(tac_ctx* c, int code, const std::string& msg) {
-    if (c) c->err = msg; else g_create_error = msg;
+int fail(tac_ctx*, int code, const std::string& msg) {
+    g_error = msg;
     return code;
 }
 #define CU(call)                                                                                              \
@@ -88,6 +113,7 @@ int fail(tac_ctx* c, int code, const std::string& msg) {
         cudaError_t e__ = (call);                                                                             \
         if (e__ != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
     } while (0)
+#define LOCK(ctx) std::lock_guard<std::recursive_mutex> lock__((ctx)->mu)
 #define TRY(call)              \
     do {                       \
         int rc__ = (call);     \
@@ -115,6 +141,23 @@ int post_launch(tac_ctx* ctx, const char* what) {
 }
 bool supported_shape(const TacParams& p) {
     return (p.N == 512 && p.k == 4) || (p.N == 1024 && p.k == 2);
+}
+
+// Constraints of the kernels beyond (N, k); violating any of them used to give silently wrong ciphertexts.
+std::string unsupported_params(const TacParams& p) {
+    const long big = (long)p.k * p.N;
+    if (p.n < 1 || p.n > 2048) return "lwe_dimension out of range";
+    if ((p.n & 1) == 0) return "lwe_dimension must be odd (the integer GEMM works on column pairs of the (n+1)-wide keyswitch key)";
+    if (p.pbs_l < 1 || p.pbs_l > 4 || p.pbs_b < 1 || p.pbs_b > 15 || p.pbs_b * p.pbs_l > 63)
+        return "pbs decomposition: need level <= 4, base_log <= 15 (digits are cached as 16-bit fields)";
+    if (p.cbs_l != 1) return "cbs_level != 1 (multi-level circuit bootstrapping) is not supported";
+    if (p.cbs_b < 1 || p.cbs_b > 15) return "cbs_base_log must be in [1, 15]";
+    if (p.ks_l < 1 || p.ks_b < 1 || p.ks_b > 7 || p.ks_b * p.ks_l > 63) return "keyswitch decomposition: base_log must be <= 7 (one byte limb on the tensor cores)";
+    if (p.pfks_l < 1 || p.pfks_b < 1 || p.pfks_b > 31 || p.pfks_b * p.pfks_l > 63) return "pfks decomposition: base_log must be <= 31";
+    // s32 tensor-memory accumulators hold 2 byte-limb products per k: exact while K·2·255² < 2^31
+    if (big * p.ks_l >= 16000 || (big + 1) * p.pfks_l >= 16000) return "decomposed length K = dim·level must stay below 16000 (s32 accumulators of the byte-limb GEMM)";
+    if (p.max_noise_sq < 1) return "max_noise_level_squared must be positive";
+    return "";
 }
 
 // ---------------------------------------------------------------------------------------------- launch wrappers
@@ -191,7 +234,6 @@ int stage_event(tac_ctx* ctx, int idx) {
     return TAC_OK;
 }
 
-constexpr uint32_t kFixCap = 1u << 16;
 // exact integer GEMM on the 5th-generation tensor cores (kernels_gemm_umma.cuh); DA / KP are operand tiles
 template <int NLIMB>
 int gemm_umma(tac_ctx* ctx, const uint8_t* DA, int nct, const uint8_t* KP, int W, int nkeys, int nkb, const uint64_t* corr,
@@ -229,18 +271,21 @@ int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     CU(cudaMemsetAsync(ctx->pfks_fix, 0, 4, ctx->stream));
     uint8_t* DA = ctx->ws_pfdig.as<uint8_t>();
     umma_digit_tiles_kernel<<<grid1d((size_t)mpad * nkb * 2, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-        in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, 0, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), kFixCap);
+        in, nct, mpad, big1, p.pfks_b, p.pfks_l, Kd, nkb, 0, DA, ctx->pfks_fix, reinterpret_cast<uint2*>(ctx->pfks_fix + 2), ctx->fix_cap);
     TRY(post_launch(ctx, "umma_digit_tiles_kernel(pfks)"));
     TRY(gemm_umma<2>(ctx, DA, nct, ctx->pfks_planes, W, ctx->G(), nkb, ctx->pfks_corr, nullptr, 0, ggsw));
-    pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), kFixCap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
-    return post_launch(ctx, "pfks_fixup_kernel");
+    pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), ctx->fix_cap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
+    TRY(post_launch(ctx, "pfks_fixup_kernel"));
+    // more ties than the list holds (crafted / trivial inputs): this kernel re-derives them all; otherwise it returns at once
+    pfks_fixup_scan_kernel<<<dim3((ctx->G() * W + 255) / 256, nct), 256, 0, ctx->stream>>>(ctx->pfks_fix, ctx->fix_cap, in, big1, p.pfks_b, p.pfks_l, ctx->pfpksk, Kd,
+                                                                                            W, ctx->G(), ggsw);
+    return post_launch(ctx, "pfks_fixup_scan_kernel");
 }
 
 // the whole circuit bootstrap for `nbox` boxes resident on the device
 int wopbs_dev(tac_ctx* ctx, const Lut& lut, int nbox, const uint64_t* in, uint64_t* out) {
     const TacParams& p = ctx->p;
     if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
-    if (p.cbs_l != 1) return fail(ctx, TAC_ERR_ARG, "cbs_level != 1 is not supported");
     const int big1 = ctx->big() + 1, G = ctx->G(), M = p.N / 2;
     const size_t ggsw_words = (size_t)G * G * p.N;
     const int max_boxes = (int)std::max<size_t>(1, ctx->max_cts / lut.n_in);
@@ -321,13 +366,17 @@ int ensure_aes_luts(tac_ctx* ctx) {
 // =================================================================================================== C ABI
 extern "C" {
 
-const char* tac_last_error(tac_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* tac_last_error(tac_ctx*) { return g_error.c_str(); }
 
 tac_ctx* tac_ctx_create(const tac_params* pp, int device) {
     tac_ctx* ctx = nullptr;     // for the CU macro's fail(ctx, …) before allocation
-    auto bail = [&](const std::string& m) -> tac_ctx* { g_create_error = m; delete ctx; return nullptr; };
+    auto bail = [&](const std::string& m) -> tac_ctx* { g_error = m; delete ctx; return nullptr; };
     const TacParams p = *reinterpret_cast<const TacParams*>(pp);
     if (!supported_shape(p)) return bail("unsupported (polynomial_size, glwe_dimension): kernels are instantiated for (512,4) and (1024,2)");
+    {   // everything else the kernels assume about a caller-supplied parameter block (the four presets satisfy all of it)
+        const std::string why = unsupported_params(p);
+        if (!why.empty()) return bail("unsupported parameter set: " + why);
+    }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) return bail(std::string("no CUDA device: ") + cudaGetErrorString(e));
@@ -342,12 +391,12 @@ tac_ctx* tac_ctx_create(const tac_params* pp, int device) {
     if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     ctx->own_stream = true;
     if (const char* s = getenv("TAC_MAX_CTS")) { const long v = atol(s); if (v > 0) ctx->max_cts = (size_t)v; }
+    if (const char* s = getenv("TAC_FIX_CAP")) { const long v = atol(s); if (v >= 0 && (uint32_t)v <= kFixCap) ctx->fix_cap = (uint32_t)v; }
     // combined twist/twiddle table in extended precision
-    const int M = p.N / 2;
-    std::vector<cplx> w(M);
+    std::vector<cplx> w(tab_len(p.N));
     build_wT(p.N, w.data());
-    if (cudaMalloc(&ctx->wT, M * sizeof(cplx)) != cudaSuccess) return bail("cudaMalloc(tables) failed");
-    cudaMemcpy(ctx->wT, w.data(), M * sizeof(cplx), cudaMemcpyHostToDevice);
+    if (cudaMalloc(&ctx->wT, w.size() * sizeof(cplx)) != cudaSuccess) return bail("cudaMalloc(tables) failed");
+    cudaMemcpy(ctx->wT, w.data(), w.size() * sizeof(cplx), cudaMemcpyHostToDevice);
     return ctx;
 }
 
@@ -368,16 +417,18 @@ void tac_ctx_destroy(tac_ctx* ctx) {
 }
 
 int tac_ctx_set_stream(tac_ctx* ctx, void* s) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (ctx->own_stream && ctx->stream) { CU(cudaStreamSynchronize(ctx->stream)); CU(cudaStreamDestroy(ctx->stream)); }
     ctx->stream = reinterpret_cast<cudaStream_t>(s);
     ctx->own_stream = false;
     return TAC_OK;
 }
-int tac_ctx_sync(tac_ctx* ctx) { CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return TAC_OK; }
+int tac_ctx_sync(tac_ctx* ctx) { LOCK(ctx); CU(cudaSetDevice(ctx->device)); CU(cudaStreamSynchronize(ctx->stream)); return TAC_OK; }
 int tac_ctx_sm_count(tac_ctx* ctx) { return ctx->sm_count; }
-int tac_ctx_set_profiling(tac_ctx* ctx, int on) { ctx->profiling = on != 0; return TAC_OK; }
+int tac_ctx_set_profiling(tac_ctx* ctx, int on) { LOCK(ctx); ctx->profiling = on != 0; return TAC_OK; }
 int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5], int* n_passes) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int s = 0; s < ST_COUNT; s++) out_ms[s] = 0.f;
@@ -393,6 +444,7 @@ int tac_ctx_stage_times(tac_ctx* ctx, float out_ms[5], int* n_passes) {
 }
 // FP64 FMA pipe peak of this GPU (the roofline denominator of the PBS kernel; not in MEASURED_PEAKS.json)
 int tac_bench_fp64_peak(tac_ctx* ctx, double* tflops) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     TRY(ensure(ctx, ctx->ws_misc, 1 << 20));
     cudaEvent_t e0, e1;
@@ -414,9 +466,10 @@ int tac_bench_fp64_peak(tac_ctx* ctx, double* tflops) {
     *tflops = best;
     return TAC_OK;
 }
-uint64_t tac_ctx_launch_count(tac_ctx* ctx) { return ctx->launches; }
+uint64_t tac_ctx_launch_count(tac_ctx* ctx) { LOCK(ctx); return ctx->launches; }
 
 int tac_ctx_alloc_keys(tac_ctx* ctx) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (ctx->keys_allocated) return TAC_OK;
     CU(cudaMalloc(&ctx->bsk_f, ctx->bsk_cplx() * sizeof(cplx)));
@@ -436,6 +489,7 @@ int tac_ctx_alloc_keys(tac_ctx* ctx) {
     return TAC_OK;
 }
 int tac_ctx_key_buffer(tac_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
+    LOCK(ctx);
     if (!ctx->keys_allocated) return fail(ctx, TAC_ERR_STATE, "key buffers not allocated");
     switch (which) {
         case 0: *dev_ptr = ctx->bsk_f; *bytes = ctx->bsk_cplx() * sizeof(cplx); return TAC_OK;
@@ -446,6 +500,7 @@ int tac_ctx_key_buffer(tac_ctx* ctx, int which, void** dev_ptr, size_t* bytes) {
 }
 // correction rows: corr[col] = (B/2)·Σ_k key[k][col], obtained by running the GEMM on constant digits B/2
 int tac_ctx_keys_ready(tac_ctx* ctx) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (!ctx->keys_allocated) return fail(ctx, TAC_ERR_STATE, "key buffers not allocated");
     const TacParams& p = ctx->p;
@@ -481,6 +536,7 @@ int tac_ctx_keys_ready(tac_ctx* ctx) {
     return TAC_OK;
 }
 int tac_ctx_upload_keys(tac_ctx* ctx, const uint64_t* bsk_std, const uint64_t* ksk, const uint64_t* pfpksk) {
+    LOCK(ctx);
     TRY(tac_ctx_alloc_keys(ctx));
     const TacParams& p = ctx->p;
     CU(cudaMemcpyAsync(ctx->ksk, ksk, ctx->ksk_words() * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -499,6 +555,7 @@ int tac_ctx_upload_keys(tac_ctx* ctx, const uint64_t* bsk_std, const uint64_t* k
 }
 
 int tac_lut_register(tac_ctx* ctx, int n_in, int n_out, const uint64_t* table, size_t len) {
+    LOCK(ctx);
     if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, TAC_ERR_CUDA, "cudaSetDevice");
     const size_t per = tac_lut_len(n_in, ctx->p.N);
     if (n_in <= 0 || n_in > 16 || n_out <= 0 || n_out > 64 || len != per * (size_t)n_out) return fail(ctx, TAC_ERR_ARG, "LUT shape does not match (n_in, n_out, N)");
@@ -510,6 +567,7 @@ int tac_lut_register(tac_ctx* ctx, int n_in, int n_out, const uint64_t* table, s
 }
 
 int tac_wopbs_batch_dev(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_dev, uint64_t* out_dev) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
     if (batch < 0) return fail(ctx, TAC_ERR_ARG, "negative batch");
@@ -517,6 +575,7 @@ int tac_wopbs_batch_dev(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_
     return wopbs_dev(ctx, *lut, batch, in_dev, out_dev);
 }
 int tac_wopbs_batch(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
     if (batch < 0) return fail(ctx, TAC_ERR_ARG, "negative batch");
@@ -532,7 +591,97 @@ int tac_wopbs_batch(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host
     return TAC_OK;
 }
 
+// Coalescing form of tac_wopbs_batch for callers that arrive one SBOX at a time from many threads (the reference's rayon
+// fan-out over 16 bytes × blocks).  The first caller to find no leader becomes the leader: it waits `window` µs for
+// company, takes everything queued, runs ONE batched pass per LUT and hands the results back; callers that arrive while a
+// pass is running queue up for the next leader.  Every caller blocks until its own request is done.
+int tac_ctx_set_coalescing(tac_ctx* ctx, int window_us, int max_batch) {
+    std::lock_guard<std::mutex> lk(ctx->q_mu);
+    if (window_us < 0 || max_batch < 1) return fail(ctx, TAC_ERR_ARG, "coalescing window / batch out of range");
+    ctx->q_window_us = window_us; ctx->q_max_batch = max_batch;
+    return TAC_OK;
+}
+int tac_ctx_coalescing_stats(tac_ctx* ctx, uint64_t* requests, uint64_t* passes) {
+    std::lock_guard<std::mutex> lk(ctx->q_mu);
+    if (requests) *requests = ctx->q_requests;
+    if (passes) *passes = ctx->q_passes;
+    return TAC_OK;
+}
+static void run_coalesced_group(tac_ctx* ctx, std::vector<PendingWopbs*>& grp) {
+    LOCK(ctx);
+    auto finish = [&](int rc) { for (auto* r : grp) { r->rc = rc; if (rc) r->err = g_error; } };
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return finish(fail(ctx, TAC_ERR_CUDA, "cudaSetDevice"));
+    const Lut* lut;
+    if (int rc = get_lut(ctx, grp[0]->lut_id, &lut)) return finish(rc);
+    const size_t big1 = (size_t)ctx->big() + 1, in_ct = (size_t)lut->n_in * big1 * 8, out_ct = (size_t)lut->n_out * big1 * 8;
+    size_t total = 0;
+    for (auto* r : grp) total += (size_t)r->batch;
+    if (int rc = ensure(ctx, ctx->ws_in, total * in_ct)) return finish(rc);
+    if (int rc = ensure(ctx, ctx->ws_out, total * out_ct)) return finish(rc);
+    auto cu = [&](cudaError_t e, const char* what) { return e == cudaSuccess ? 0 : fail(ctx, TAC_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e)); };
+    size_t off = 0;
+    for (auto* r : grp) {
+        if (int rc = cu(cudaMemcpyAsync(ctx->ws_in.as<uint8_t>() + off * in_ct, r->in, (size_t)r->batch * in_ct, cudaMemcpyHostToDevice, ctx->stream), "H2D")) return finish(rc);
+        off += (size_t)r->batch;
+    }
+    if (int rc = wopbs_dev(ctx, *lut, (int)total, ctx->ws_in.as<uint64_t>(), ctx->ws_out.as<uint64_t>())) return finish(rc);
+    off = 0;
+    for (auto* r : grp) {
+        if (int rc = cu(cudaMemcpyAsync(r->out, ctx->ws_out.as<uint8_t>() + off * out_ct, (size_t)r->batch * out_ct, cudaMemcpyDeviceToHost, ctx->stream), "D2H")) return finish(rc);
+        off += (size_t)r->batch;
+    }
+    finish(cu(cudaStreamSynchronize(ctx->stream), "cudaStreamSynchronize"));
+}
+int tac_wopbs_coalesced(tac_ctx* ctx, int lut_id, int batch, const uint64_t* in_host, uint64_t* out_host) {
+    if (batch < 0) return fail(ctx, TAC_ERR_ARG, "negative batch");
+    if (batch == 0) return TAC_OK;
+    PendingWopbs me{lut_id, batch, in_host, out_host};
+    std::unique_lock<std::mutex> lk(ctx->q_mu);
+    ctx->q_pending.push_back(&me);
+    ctx->q_requests++;
+    ctx->q_cv.notify_all();
+    for (;;) {
+        ctx->q_cv.wait(lk, [&] { return me.done || !ctx->q_leader; });
+        if (me.done) break;
+        // become the leader of the next pass
+        ctx->q_leader = true;
+        if (ctx->q_window_us > 0) {
+            const auto deadline = std::chrono::steady_clock::now() + std::chrono::microseconds(ctx->q_window_us);
+            size_t seen = 0;
+            // keep waiting while requests are still arriving, at most `window` after the last arrival check
+            while (ctx->q_cv.wait_until(lk, deadline, [&] { return ctx->q_pending.size() != seen; })) {
+                seen = ctx->q_pending.size();
+                size_t cts = 0;
+                for (auto* r : ctx->q_pending) cts += (size_t)r->batch;
+                if (cts >= (size_t)ctx->q_max_batch) break;
+            }
+        }
+        std::vector<PendingWopbs*> mine;
+        mine.swap(ctx->q_pending);
+        lk.unlock();
+        // one pass per distinct LUT, in arrival order
+        std::vector<bool> used(mine.size(), false);
+        size_t n_groups = 0;
+        for (size_t i = 0; i < mine.size(); i++) {
+            if (used[i]) continue;
+            std::vector<PendingWopbs*> grp;
+            for (size_t j = i; j < mine.size(); j++)
+                if (!used[j] && mine[j]->lut_id == mine[i]->lut_id) { used[j] = true; grp.push_back(mine[j]); }
+            run_coalesced_group(ctx, grp);
+            n_groups++;
+        }
+        lk.lock();
+        ctx->q_passes += n_groups;
+        for (auto* r : mine) r->done = true;
+        ctx->q_leader = false;
+        ctx->q_cv.notify_all();
+    }
+    if (me.rc) g_error = me.err;
+    return me.rc;
+}
+
 int tac_lwe_add_batch_dev(tac_ctx* ctx, uint64_t* a, const uint64_t* b, size_t n_cts) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t total = n_cts * ((size_t)ctx->big() + 1);
     if (total == 0) return TAC_OK;
@@ -540,6 +689,7 @@ int tac_lwe_add_batch_dev(tac_ctx* ctx, uint64_t* a, const uint64_t* b, size_t n
     return post_launch(ctx, "lwe_add_kernel");
 }
 int tac_lwe_add_batch(tac_ctx* ctx, uint64_t* a_host, const uint64_t* b_host, size_t n_cts) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = n_cts * ((size_t)ctx->big() + 1) * 8;
     if (bytes == 0) return TAC_OK;
@@ -555,6 +705,7 @@ int tac_lwe_add_batch(tac_ctx* ctx, uint64_t* a_host, const uint64_t* b_host, si
 
 // ------------------------------------------------------------------------------------------------ fused AES
 int tac_aes_set_key_schedule(tac_ctx* ctx, const uint64_t* ks_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const size_t bytes = (size_t)44 * 32 * (ctx->big() + 1) * 8;
     if (!ctx->key_sched) CU(cudaMalloc(&ctx->key_sched, bytes));
@@ -565,12 +716,14 @@ int tac_aes_set_key_schedule(tac_ctx* ctx, const uint64_t* ks_host) {
     return TAC_OK;
 }
 int tac_aes_key_schedule_buffer(tac_ctx* ctx, void** dev_ptr, size_t* bytes) {
+    LOCK(ctx);
     TRY(tac_aes_set_key_schedule(ctx, nullptr));
     *dev_ptr = ctx->key_sched; *bytes = (size_t)44 * 32 * (ctx->big() + 1) * 8;
     return TAC_OK;
 }
 
 int tac_aes_encrypt_blocks_dev(tac_ctx* ctx, int n_blocks, int rounds, int in_noise_sq, const uint64_t* in_dev, uint64_t* out_dev) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (!ctx->key_sched) return fail(ctx, TAC_ERR_STATE, "no key schedule on the device (tac_aes_set_key_schedule)");
     if (n_blocks < 0 || rounds < 1 || rounds > 10) return fail(ctx, TAC_ERR_ARG, "n_blocks / rounds out of range");
@@ -600,6 +753,7 @@ int tac_aes_encrypt_blocks_dev(tac_ctx* ctx, int n_blocks, int rounds, int in_no
     return post_launch(ctx, "aes_final_round_kernel");
 }
 int tac_aes_encrypt_blocks(tac_ctx* ctx, int n_blocks, int rounds, int in_noise_sq, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (n_blocks <= 0) return n_blocks == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative n_blocks");
     const size_t bytes = (size_t)n_blocks * 128 * (ctx->big() + 1) * 8;
@@ -614,6 +768,7 @@ int tac_aes_encrypt_blocks(tac_ctx* ctx, int n_blocks, int rounds, int in_noise_
 
 // fhe_sbox_gal_mul_pbs::key_schedule (:134-164) with boot_word (:166-180) and sub_word (:182-191) on the device
 int tac_aes_key_schedule(tac_ctx* ctx, const uint64_t* key_bits_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (8 + 1 > ctx->p.max_noise_sq) return fail(ctx, TAC_ERR_NOISE, "NoiseTooBig: key schedule needs max_noise_level_squared >= 9");
     TRY(ensure_aes_luts(ctx));
@@ -657,6 +812,7 @@ int tac_aes_key_schedule(tac_ctx* ctx, const uint64_t* key_bits_host, uint64_t* 
 
 // ------------------------------------------------------------------------------------------------ single stages
 int tac_stage_keyswitch(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
     if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
@@ -669,6 +825,7 @@ int tac_stage_keyswitch(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* 
     return TAC_OK;
 }
 int tac_stage_pbs(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
     if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
@@ -681,6 +838,7 @@ int tac_stage_pbs(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_ho
     return TAC_OK;
 }
 int tac_stage_pfks(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
     if (n <= 0) return n == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
@@ -693,9 +851,9 @@ int tac_stage_pfks(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_h
     return TAC_OK;
 }
 int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64_t* ggsw_std_host, uint64_t* out_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
-    if (ctx->p.cbs_l != 1) return fail(ctx, TAC_ERR_ARG, "cbs_level != 1 is not supported");
     if (batch <= 0) return batch == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative batch");
     const int G = ctx->G(), M = ctx->p.N / 2;
     const size_t nct = (size_t)batch * lut->n_in;
@@ -709,7 +867,40 @@ int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64
     return TAC_OK;
 }
 
+int tac_stage_poly_fft(tac_ctx* ctx, size_t n_polys, const uint64_t* polys_host, double* out_host) {
+    LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    if (n_polys == 0) return TAC_OK;
+    const size_t N = ctx->p.N, M = N / 2;
+    TRY(ensure(ctx, ctx->ws_ggsw, n_polys * N * 8)); TRY(ensure(ctx, ctx->ws_ggswf, n_polys * M * sizeof(cplx)));
+    CU(cudaMemcpyAsync(ctx->ws_ggsw.p, polys_host, n_polys * N * 8, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), n_polys, ctx->ws_ggswf.as<cplx>()));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_ggswf.p, n_polys * M * sizeof(cplx), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+int tac_fft_slot_frequencies(int polynomial_size, int32_t* freq) {
+    if (polynomial_size != 512 && polynomial_size != 1024) return TAC_ERR_ARG;
+    const int M = polynomial_size / 2, P = M / 16;
+    for (int q = 0; q < P; q++)
+        for (int r = 0; r < 16; r++) freq[slot_of(q, r)] = q + P * r;
+    return TAC_OK;
+}
+int tac_stage_sample_extract(tac_ctx* ctx, size_t n_glwe, const uint64_t* glwe_host, uint64_t* out_host) {
+    LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    if (n_glwe == 0) return TAC_OK;
+    const size_t ib = n_glwe * ctx->G() * ctx->p.N * 8, ob = n_glwe * ((size_t)ctx->big() + 1) * 8;
+    TRY(ensure(ctx, ctx->ws_ggsw, ib)); TRY(ensure(ctx, ctx->ws_out, ob));
+    CU(cudaMemcpyAsync(ctx->ws_ggsw.p, glwe_host, ib, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(check_launch(ctx, ctx->ops->sample_extract(klaunch(ctx), ctx->ws_ggsw.as<uint64_t>(), n_glwe, ctx->ws_out.as<uint64_t>()), "sample_extract_kernel"));
+    CU(cudaMemcpyAsync(out_host, ctx->ws_out.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+
 int tac_stage_cmux_rotate(tac_ctx* ctx, int levels, int base_log, const uint64_t* ggsw_std_host, int n_acc, const int32_t* rot, uint64_t* acc_host) {
+    LOCK(ctx);
     CU(cudaSetDevice(ctx->device));
     if (n_acc <= 0) return n_acc == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
     const TacParams& p = ctx->p;

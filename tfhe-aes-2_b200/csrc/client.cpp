@@ -14,6 +14,8 @@
 #include <cmath>
 #include <cstring>
 #include <thread>
+#include <cstdio>
+#include <sys/random.h>
 #include <vector>
 
 namespace {
@@ -23,12 +25,12 @@ struct Stream {
     uint32_t in[16];
     uint32_t out[16];
     int used = 16;
-    Stream(uint64_t seed, uint32_t domain, uint64_t nonce) {
+    // master: 256-bit ChaCha key of this client (OS entropy, or derived from a test seed); bytes 8..11 separate the domains
+    Stream(const uint8_t master[32], uint32_t domain, uint64_t nonce) {
         static const uint32_t sigma[4] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u};
         uint8_t key[32];
-        for (int i = 0; i < 8; i++) key[i] = (uint8_t)(seed >> (8 * i));
-        for (int i = 0; i < 4; i++) key[8 + i] = (uint8_t)(domain >> (8 * i));
-        memcpy(key + 12, "tfhe-aes-b200 rng v1", 20);
+        memcpy(key, master, 32);
+        for (int i = 0; i < 4; i++) key[8 + i] ^= (uint8_t)(domain >> (8 * i));
         memcpy(in, sigma, 16);
         memcpy(in + 4, key, 32);          // little-endian host
         in[12] = 0; in[13] = 0;
@@ -96,9 +98,31 @@ void parallel_for(long count, int threads, F f) {
     for (auto& th : pool) th.join();
 }
 
+// Deterministic (test / benchmark) master key: seed ‖ 0000 ‖ fixed label.  Anyone who knows the seed can recompute the
+// secret keys, so this mode is for reproducible tests only; tac_client_keygen_os draws all 256 bits from the OS.
+void master_from_seed(uint64_t seed, uint8_t master[32]) {
+    for (int i = 0; i < 8; i++) master[i] = (uint8_t)(seed >> (8 * i));
+    memset(master + 8, 0, 4);
+    memcpy(master + 12, "tfhe-aes-b200 rng v1", 20);
+}
+bool master_from_os(uint8_t master[32]) {
+    size_t got = 0;
+    while (got < 32) {
+        const ssize_t r = getrandom(master + got, 32 - got, 0);
+        if (r <= 0) break;
+        got += (size_t)r;
+    }
+    if (got == 32) return true;
+    FILE* f = fopen("/dev/urandom", "rb");
+    if (!f) return false;
+    const bool ok = fread(master, 1, 32, f) == 32;
+    fclose(f);
+    return ok;
+}
+
 struct Client {
     TacParams p;
-    uint64_t seed;
+    uint8_t seed[32];              // master key of every random stream of this client
     std::vector<uint64_t> sk_glwe, sk_lwe, bsk, ksk, pfpksk;
     std::vector<std::vector<int>> glwe_support;   // positions of the 1-bits of each GLWE key polynomial
     bool have_eval = false;
@@ -195,19 +219,44 @@ int tac_generate_lut(int n_in, int n_out, int N, const uint64_t* f_table, uint64
 
 size_t tac_key_len(const tac_params* p, int which) { return key_len(*reinterpret_cast<const TacParams*>(p), which); }
 
-tac_client_key* tac_client_keygen(const tac_params* pp, uint64_t seed) {
-    Client* c = new Client();
-    c->p = *reinterpret_cast<const TacParams*>(pp);
-    c->seed = seed;
-    const int big = c->big();
-    c->sk_glwe.resize(big);
-    c->sk_lwe.resize(c->p.n);
-    { Stream r(seed, DOM_SK_GLWE, 0); for (auto& w : c->sk_glwe) w = r.u64() & 1ull; }
-    { Stream r(seed, DOM_SK_LWE, 0); for (auto& w : c->sk_lwe) w = r.u64() & 1ull; }
-    c->glwe_support.resize(c->p.k);
+static void index_glwe_support(Client* c) {
+    c->glwe_support.assign(c->p.k, {});
     for (int i = 0; i < c->p.k; i++)
         for (int t = 0; t < c->p.N; t++)
             if (c->sk_glwe[(size_t)i * c->p.N + t]) c->glwe_support[i].push_back(t);
+}
+static tac_client_key* client_new(const tac_params* pp, const uint8_t master[32]) {
+    Client* c = new Client();
+    c->p = *reinterpret_cast<const TacParams*>(pp);
+    memcpy(c->seed, master, 32);
+    c->sk_glwe.resize(c->big());
+    c->sk_lwe.resize(c->p.n);
+    { Stream r(c->seed, DOM_SK_GLWE, 0); for (auto& w : c->sk_glwe) w = r.u64() & 1ull; }
+    { Stream r(c->seed, DOM_SK_LWE, 0); for (auto& w : c->sk_lwe) w = r.u64() & 1ull; }
+    index_glwe_support(c);
+    return reinterpret_cast<tac_client_key*>(c);
+}
+tac_client_key* tac_client_keygen(const tac_params* pp, uint64_t seed) {
+    uint8_t master[32];
+    master_from_seed(seed, master);
+    return client_new(pp, master);
+}
+tac_client_key* tac_client_keygen_os(const tac_params* pp) {
+    uint8_t master[32];
+    if (!master_from_os(master)) return nullptr;
+    return client_new(pp, master);
+}
+tac_client_key* tac_client_from_secret_keys(const tac_params* pp, const uint64_t* sk_glwe, const uint64_t* sk_lwe) {
+    uint8_t master[32];
+    if (!master_from_os(master)) return nullptr;               // encryption masks / noise of this instance: fresh entropy
+    Client* c = new Client();
+    c->p = *reinterpret_cast<const TacParams*>(pp);
+    memcpy(c->seed, master, 32);
+    c->sk_glwe.assign(sk_glwe, sk_glwe + c->big());
+    c->sk_lwe.assign(sk_lwe, sk_lwe + c->p.n);
+    for (uint64_t w : c->sk_glwe) if (w > 1) { delete c; return nullptr; }
+    for (uint64_t w : c->sk_lwe) if (w > 1) { delete c; return nullptr; }
+    index_glwe_support(c);
     return reinterpret_cast<tac_client_key*>(c);
 }
 void tac_client_free(tac_client_key* ck) { delete reinterpret_cast<Client*>(ck); }

@@ -7,14 +7,17 @@
 // arithmetic (FFT passes, swizzles, slot order, rotation, decomposition) is validated without a GPU.
 //
 // FFT: a negacyclic size-N real transform is a size-M = N/2 complex FFT of (p[j] + i·p[j+M])·e^{iπj/N}.  M = 16·P and
-// one FFT is done by 16 threads in two register passes (DFT-P over the stride-16 samples, twiddle, transpose through
-// shared memory, DFT-16).  The Fourier "slot" order produced by the forward transform is arbitrary but fixed; the
-// Fourier-domain keys are produced by the same forward routine, all Fourier-domain work is pointwise, and the inverse
-// transform consumes the same order.
+// one FFT is done by 16 threads in two register passes (DFT-P over the stride-16 samples, transpose through shared
+// memory, DFT-16).  Both passes of the forward transform are decimation-in-time with the twiddle applied before the add,
+// so the twist and the inter-pass twiddle are folded into the butterflies and every butterfly is 6 FMAs (see bfly_r).
+// The Fourier "slot" order produced by the forward transform is arbitrary but fixed; the Fourier-domain keys are
+// produced by the same forward routine, all Fourier-domain work is pointwise, and the inverse transform consumes the
+// same order.
 //
-//   slot σ = q·16 + (i ^ (q & 15))  holds frequency  f = q + P·bitrev4(i)        (q < P, i < 16)
+//   slot σ = q·16 + (r ^ (q & 15))  holds frequency  f = q + P·r        (q < P, r < 16)
 #pragma once
 #include "tac_common.h"
+#include <cmath>
 #include <cstring>
 #include <type_traits>
 
@@ -27,11 +30,13 @@ struct alignas(16) cplx { double x, y; };
 #endif
 
 TAC_HD cplx mk(double x, double y) { cplx r; r.x = x; r.y = y; return r; }
-TAC_HD cplx cmul(cplx a, cplx b) { return mk(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-TAC_HD cplx cmul_conj(cplx a, cplx b) { return mk(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); }   // a * conj(b)
+TAC_HD cplx cmul(cplx a, cplx b) { return mk(fma(-a.y, b.y, a.x * b.x), fma(a.y, b.x, a.x * b.y)); }
+TAC_HD cplx cmul_conj(cplx a, cplx b) { return mk(fma(a.y, b.y, a.x * b.x), fma(-a.x, b.y, a.y * b.x)); }   // a * conj(b)
+// o += a·b.  The order of the four FMAs is part of the contract: every MAC variant (one thread per slot, or the real /
+// imaginary split over a lane pair) accumulates in exactly this order, so all of them produce the same words.
 TAC_HD void cfma(cplx& o, cplx a, cplx b) {
-    o.x += a.x * b.x; o.x -= a.y * b.y;
-    o.y += a.x * b.y; o.y += a.y * b.x;
+    o.x = fma(a.x, b.x, o.x); o.x = fma(-a.y, b.y, o.x);
+    o.y = fma(a.y, b.x, o.y); o.y = fma(a.x, b.y, o.y);
 }
 
 // 2^52 + f for a small unsigned integer f, without an int→double conversion instruction
@@ -93,64 +98,92 @@ TAC_HD cplx mul_w128(cplx d) {
         const double wr = (K < 32) ? cos128<(K < 32 ? K : 0)>() : -cos128<(K >= 32 ? 64 - K : 0)>();
         const double ws = (K < 32) ? cos128<(K < 32 ? 32 - K : 0)>() : cos128<(K >= 32 ? K - 32 : 0)>();
         const double wi = INV ? ws : -ws;
-        return mk(d.x * wr - d.y * wi, d.x * wi + d.y * wr);
+        return mk(fma(-d.y, wi, d.x * wr), fma(d.y, wr, d.x * wi));
     }
 }
+// cos / sin of 2π·A/128 for any integer A, from the first-quadrant table
+template <int A>
+TAC_HD double cosq() {
+    constexpr int a = ((A % 128) + 128) % 128;
+    if constexpr (a <= 32) return cos128<(a <= 32 ? a : 0)>();
+    else if constexpr (a <= 64) return -cos128<(a > 32 && a <= 64 ? 64 - a : 0)>();
+    else if constexpr (a <= 96) return -cos128<(a > 64 && a <= 96 ? a - 64 : 0)>();
+    else return cos128<(a > 96 ? 128 - a : 0)>();
+}
+template <int A> TAC_HD double sinq() { return cosq<A - 32>(); }
 
-// in-register DFT, P ∈ {16, 32}.  Forward: DIF, natural in → bit-reversed out.  Inverse: DIT, bit-reversed in → natural
-// out, unnormalised.
-template <int P, int LEN>
-TAC_HD void dft_fwd_stage(cplx* v) {
-    constexpr int half = LEN / 2, tstep = 128 / LEN;
-    static_for<0, P, LEN>([&](auto sc) {
-        static_for<0, half>([&](auto jc) {
-            constexpr int s = decltype(sc)::value, j = decltype(jc)::value;
-            const cplx u = v[s + j], w = v[s + j + half];
-            v[s + j] = mk(u.x + w.x, u.y + w.y);
-            v[s + j + half] = mul_w128<false, j * tstep>(mk(u.x - w.x, u.y - w.y));
-        });
-    });
-    if constexpr (LEN > 2) dft_fwd_stage<P, LEN / 2>(v);
+// Radix-2 butterfly with the twiddle applied BEFORE the add (decimation in time), fused:
+//     (u, w) ← (u + T·w, u − T·w)        a = u + T·w in 4 FMAs, u − T·w = 2u − a in 2 FMAs
+// (a separate complex multiply followed by an add and a subtract costs 2 DMUL + 2 DFMA + 4 DADD).  T = exp(2πi·A/128)
+// is a compile-time constant taken from the constant bank, or a run-time value (lane-dependent twiddles).
+TAC_HD void bfly_r(cplx& u, cplx& w, const cplx T) {
+    const double ax = fma(-T.y, w.y, fma(T.x, w.x, u.x));
+    const double ay = fma(T.y, w.x, fma(T.x, w.y, u.y));
+    w = mk(fma(2.0, u.x, -ax), fma(2.0, u.y, -ay));
+    u = mk(ax, ay);
 }
-template <int P> TAC_HD void dft_fwd(cplx* v) { dft_fwd_stage<P, P>(v); }
-template <int P, int LEN>
-TAC_HD void dft_inv_stage(cplx* v) {
-    constexpr int half = LEN / 2, tstep = 128 / LEN;
-    static_for<0, P, LEN>([&](auto sc) {
-        static_for<0, half>([&](auto jc) {
-            constexpr int s = decltype(sc)::value, j = decltype(jc)::value;
-            const cplx u = v[s + j];
-            const cplx w = mul_w128<true, j * tstep>(v[s + j + half]);
-            v[s + j] = mk(u.x + w.x, u.y + w.y);
-            v[s + j + half] = mk(u.x - w.x, u.y - w.y);
-        });
-    });
-    if constexpr (LEN < P) dft_inv_stage<P, LEN * 2>(v);
+template <int A>
+TAC_HD void bfly_c(cplx& u, cplx& w) {
+    constexpr int a = ((A % 128) + 128) % 128;
+    if constexpr (a == 0) { const cplx x = u; u = mk(x.x + w.x, x.y + w.y); w = mk(x.x - w.x, x.y - w.y); }
+    else if constexpr (a == 64) { const cplx x = u; u = mk(x.x - w.x, x.y - w.y); w = mk(x.x + w.x, x.y + w.y); }
+    else if constexpr (a == 32) { const cplx x = u, y = w; u = mk(x.x - y.y, x.y + y.x); w = mk(x.x + y.y, x.y - y.x); }       // T = +i
+    else if constexpr (a == 96) { const cplx x = u, y = w; u = mk(x.x + y.y, x.y - y.x); w = mk(x.x - y.y, x.y + y.x); }       // T = −i
+    else bfly_r(u, w, mk(cosq<a>(), sinq<a>()));
 }
-template <int P> TAC_HD void dft_inv(cplx* v) { dft_inv_stage<P, 2>(v); }
 template <int P> TAC_HD constexpr int bitrev(int i) {
     int r = 0;
     for (int b = 1; b < P; b <<= 1) { r = (r << 1) | (i & 1); i >>= 1; }
     return r;
 }
+// In-register decimation-in-time DFT over the P values v[bitrev(n)] = x_n, natural order out.  bf(LEN, k, u, w) performs
+// the butterfly at position k of a block of size LEN.  Every butterfly multiplies BEFORE it adds, so a geometric scaling
+// of the INPUT,  X[k] = Σ_n x_n ρ^n e^{∓2πi nk/P},  costs nothing: the block-LEN twiddle becomes ρ^{P/LEN}·e^{∓2πi k/LEN}.
+// That is how the negacyclic twist and the twiddle between the two passes of the forward transform are absorbed.
+template <int P, int LEN, class Bf>
+TAC_HD void dit_stages(cplx* v, Bf&& bf) {
+    constexpr int half = LEN / 2;
+    static_for<0, P, LEN>([&](auto sc) {
+        static_for<0, half>([&](auto kc) {
+            constexpr int s = decltype(sc)::value, k = decltype(kc)::value;
+            bf(std::integral_constant<int, LEN>{}, kc, v[s + k], v[s + k + half]);
+        });
+    });
+    if constexpr (LEN < P) dit_stages<P, LEN * 2>(v, bf);
+}
+// plain inverse DFT (e^{+2πi nk/P}), unnormalised
+template <int P> TAC_HD void dft_inv(cplx* v) {
+    dit_stages<P, 2>(v, [&](auto lc, auto kc, cplx& u, cplx& w) { bfly_c<128 * decltype(kc)::value / decltype(lc)::value>(u, w); });
+}
 TAC_HD constexpr int slot_of(int q, int i) { return q * 16 + (i ^ (q & 15)); }
 
-// The twist e^{iπj/N} of sample j = t + 16m factors as  tw_t · c_m  with  c_m = e^{iπ·16m/N} = e^{2πi·m/(N/8)}  — a
-// compile-time constant per register — and tw_t, which commutes with the DFT over m and is folded into the inter-pass
-// twiddle.  One table serves both directions:
-//     wT[slot_of(q, t)] = e^{iπt/N} · e^{-2πi·tq/M}            (M entries, swizzled like S so that both the pass-1
-//                                                                 (t across lanes) and pass-A (q across lanes) reads are conflict-free)
+// Transform layout.  Sample j = t + 16m (t < 16 the lane, m < P), frequency f = q + P·r (q < P, r < 16):
+//     Z_f = Σ_j z_j e^{iπj/N} e^{-2πi jf/M}
+//         = Σ_t e^{-2πi tr/16} · ρ_q^t · A_t(q),      A_t(q) = Σ_m z_{t+16m} · c^m · e^{-2πi mq/P}
+//     c = e^{iπ·16/N}  (compile-time),      ρ_q = e^{iπ/N} · e^{-2πi q/M}  (per lane, from a table)
+// pass 1 (lane t) computes A_t(·) with the twist folded into its butterflies, pass 2 (lane q) the outer sum with ρ_q folded.
+//     slot σ = slot_of(q, r) = q·16 + (r ^ (q & 15))   holds frequency   f = q + P·r
+// One table `wT` of N entries serves both directions:
+//     wT[slot_of(q, t)]         = ρ_q^t                                    inverse: twiddle between pass A and pass B (conjugated)
+//     wT[M + (LEN/2-1+k)·P + q] = ρ_q^{16/LEN} · e^{-2πi k/LEN}            forward pass 2: butterfly twiddles, LEN = 2,4,8,16, k < LEN/2
 // Memory-operation order.  All buffers of a CTA are carved from one dynamic shared-memory array, so the compiler must
 // assume that a store to one of them may alias a later load from another and keeps them in program order: a loop of the
 // form "load – compute – store" is executed strictly one element at a time and exposes the shared-memory latency every
 // time (measured: 16 serialised twiddle loads ≈ 400 cycles of a 1550-cycle pass, tools/fft_lat.cu; PBS kernel 119.4 → 113.4 ms).  The passes below are
 // therefore written in CHUNKS: all loads of a chunk first, then the arithmetic and the stores of the chunk.
-constexpr int kChunk = 8;        // twiddles per chunk (32 registers in flight); measured on B200: 8 → 113.4 ms, 4 or 16 → 116.5 ms
-constexpr int kLoadChunk = 4;    // operand pairs per chunk of the decomposing pass (2, 4, 8, 16 measure the same)
+#ifndef TAC_CHUNK
+#define TAC_CHUNK 8
+#endif
+#ifndef TAC_LOAD_CHUNK
+#define TAC_LOAD_CHUNK 4
+#endif
+constexpr int kChunk = TAC_CHUNK;             // twiddles per chunk (32 registers in flight); measured on B200: 8 → 113.4 ms, 4 or 16 → 116.5 ms
+constexpr int kLoadChunk = TAC_LOAD_CHUNK;    // operand pairs per chunk of the decomposing pass (2, 4, 8, 16 measure the same)
+TAC_HD constexpr int tab_len(int N) { return N; }    // entries of wT
 
-// S[slot] = v[i] · wT[slot] (forward) for the P registers of thread t, chunked
-template <int P, bool CONJ, class SlotFn>
-TAC_HD void twiddle_store(const cplx* v, SlotFn slot, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+// S[slot] = v[i] · conj(wT[slot]) for the P registers of thread t, chunked
+template <int P, class SlotFn>
+TAC_HD void twiddle_store_conj(const cplx* v, SlotFn slot, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int CH = P < kChunk ? P : kChunk;
     static_for<0, P, CH>([&](auto cc) {
         constexpr int c0 = decltype(cc)::value;
@@ -158,9 +191,18 @@ TAC_HD void twiddle_store(const cplx* v, SlotFn slot, const cplx* __restrict__ w
         static_for<0, CH>([&](auto kc) { constexpr int k = decltype(kc)::value; w[k] = wT[slot(c0 + k)]; });
         static_for<0, CH>([&](auto kc) {
             constexpr int k = decltype(kc)::value;
-            if constexpr (CONJ) { if constexpr (c0 + k == 0) S[slot(0)] = v[0]; else S[slot(c0 + k)] = cmul_conj(v[c0 + k], w[k]); }
-            else S[slot(c0 + k)] = cmul(v[c0 + k], w[k]);
+            if constexpr (c0 + k == 0) S[slot(0)] = v[0]; else S[slot(c0 + k)] = cmul_conj(v[c0 + k], w[k]);
         });
+    });
+}
+// the pass-1 DFT of the forward transform on v[bitrev(m)] = z_{t+16m}: twist c^m folded (see above)
+template <int N>
+TAC_HD void dft_fwd_twisted(cplx* v) {
+    constexpr int P = N / 32, CP = (1024 / N) * P;             // c^P = exp(2πi·CP/128)
+    dit_stages<P, 2>(v, [&](auto lc, auto kc, cplx& u, cplx& w) {
+        constexpr int LEN = decltype(lc)::value, k = decltype(kc)::value;
+        static_assert((CP - 128 * k) % LEN == 0, "twiddle not on the 128-point grid");
+        bfly_c<(CP - 128 * k) / LEN>(u, w);
     });
 }
 // ------------------------------------------------------------------------------------------------ forward, pass 1
@@ -168,8 +210,8 @@ TAC_HD void twiddle_store(const cplx* v, SlotFn slot, const cplx* __restrict__ w
 // batched per chunk), `finish(jj, raw, a, b)` turns it into the two real samples (and may store by-products).
 // Thread t (0..15) of the FFT group.
 template <int N, class Load, class Finish>
-TAC_HD void fft_fwd_pass1_2ph(int t, Load load, Finish finish, const cplx* __restrict__ wT, cplx* __restrict__ S) {
-    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;     // c_m = exp(+2πi · m·CSTEP / 128)
+TAC_HD void fft_fwd_pass1_2ph(int t, Load load, Finish finish, cplx* __restrict__ S) {
+    constexpr int M = N / 2, P = M / 16;
     constexpr int CH = kLoadChunk;
     cplx v[P];
     static_for<0, P, CH>([&](auto cc) {
@@ -180,37 +222,41 @@ TAC_HD void fft_fwd_pass1_2ph(int t, Load load, Finish finish, const cplx* __res
             constexpr int k = decltype(kc)::value, m = c0 + k;
             double a, b;
             finish(t + 16 * m, raw[k], a, b);
-            v[m] = mul_w128<true, m * CSTEP>(mk(a, b));
+            v[bitrev<P>(m)] = mk(a, b);
         });
     });
-    dft_fwd<P>(v);
-    twiddle_store<P, false>(v, [&](int i) { return slot_of(bitrev<P>(i), t); }, wT, S);
+    dft_fwd_twisted<N>(v);
+    static_for<0, P>([&](auto qc) { constexpr int q = decltype(qc)::value; S[slot_of(q, t)] = v[q]; });
 }
 // `src(jj, a, b)` yields the real samples jj and jj + M directly (sources without by-product stores)
 template <int N, class Src>
-TAC_HD void fft_fwd_pass1(int t, Src src, const cplx* __restrict__ wT, cplx* __restrict__ S) {
-    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;
+TAC_HD void fft_fwd_pass1(int t, Src src, cplx* __restrict__ S) {
+    constexpr int M = N / 2, P = M / 16;
     cplx v[P];
     static_for<0, P>([&](auto mc) {
         constexpr int m = decltype(mc)::value;
         double a, b;
         src(t + 16 * m, a, b);
-        v[m] = mul_w128<true, m * CSTEP>(mk(a, b));
+        v[bitrev<P>(m)] = mk(a, b);
     });
-    dft_fwd<P>(v);
-    twiddle_store<P, false>(v, [&](int i) { return slot_of(bitrev<P>(i), t); }, wT, S);
+    dft_fwd_twisted<N>(v);
+    static_for<0, P>([&](auto qc) { constexpr int q = decltype(qc)::value; S[slot_of(q, t)] = v[q]; });
 }
 // ------------------------------------------------------------------------------------------------ forward, pass 2 (in place)
 template <int N>
-TAC_HD void fft_fwd_pass2(int t, cplx* __restrict__ S) {
+TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int M = N / 2, P = M / 16;
+    const cplx* __restrict__ wF = wT + M;
 #pragma unroll
     for (int c2 = 0; c2 < P / 16; c2++) {
         const int q = t + 16 * c2;
         cplx v[16];
-        static_for<0, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; v[tt] = S[slot_of(q, tt)]; });
-        dft_fwd<16>(v);
-        static_for<0, 16>([&](auto ic) { constexpr int i = decltype(ic)::value; S[slot_of(q, i)] = v[i]; });
+        static_for<0, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; v[bitrev<16>(tt)] = S[slot_of(q, tt)]; });
+        dit_stages<16, 2>(v, [&](auto lc, auto kc, cplx& u, cplx& w) {
+            constexpr int LEN = decltype(lc)::value, k = decltype(kc)::value;
+            bfly_r(u, w, wF[(LEN / 2 - 1 + k) * P + q]);
+        });
+        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; S[slot_of(q, r)] = v[r]; });
     }
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass A (in place)
@@ -221,9 +267,9 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
     for (int c2 = 0; c2 < P / 16; c2++) {
         const int q = t + 16 * c2;
         cplx v[16];
-        static_for<0, 16>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = S[slot_of(q, i)]; });
+        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; v[bitrev<16>(r)] = S[slot_of(q, r)]; });
         dft_inv<16>(v);
-        twiddle_store<16, true>(v, [&](int tt) { return slot_of(q, tt); }, wT, S);
+        twiddle_store_conj<16>(v, [&](int tt) { return slot_of(q, tt); }, wT, S);
     }
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass B

@@ -5,7 +5,7 @@
 //   S     cplx    [B*G][M]        one FFT buffer per (ciphertext, polynomial); reused for the MAC output
 //   dig   uint32  [B*G][L-1][M]   decomposition digits of levels 1..L-1 of this step (level L is consumed at once),
 //                                 samples (jj, jj+M) packed as 16-bit fields digit + B/2
-//   wT    cplx    [M]             combined twist/twiddle table (ep_core.cuh)
+//   wT    cplx    [N]             twiddle tables of both directions (ep_core.cuh)
 // Per-thread registers that live across the phases of one step: out[SPT][B][G] (Fourier-domain accumulators of the
 // frequency slots this thread owns).
 //
@@ -69,8 +69,7 @@ struct MacCfg {
 // group phase 1 of a step: decompose the operand polynomial `job` (coef(jj, x0, x1) yields its coefficients jj and jj + M),
 // keep the digits of levels 1..L-1 in dig, and run forward-FFT pass 1 on the level-L digits straight from registers.
 template <class C, class CoefFn>
-TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, uint32_t* __restrict__ dig, const cplx* __restrict__ wT,
-                            cplx* __restrict__ S) {
+TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, uint32_t* __restrict__ dig, cplx* __restrict__ S) {
     uint32_t* dj = dig + (size_t)job * (C::L - 1) * C::M;
     struct Pair { uint64_t x0, x1; };
     fft_fwd_pass1_2ph<C::N>(t, [&](int jj) { Pair p; coef(jj, p.x0, p.x1); return p; },
@@ -80,16 +79,16 @@ TAC_HD void grp_decomp_fwd1(int t, int job, CoefFn coef, const DecompFast& dc, u
 #pragma unroll
             for (int s = 0; s + 1 < C::L; s++) dj[(size_t)s * C::M + jj] = w[s];
             unpack_digits(w[C::L - 1], dc, a, b);
-        }, wT, S + (size_t)job * C::M);
+        }, S + (size_t)job * C::M);
 }
 // forward FFT pass 1 of the cached level-`lev` digits (lev < L)
 template <class C>
-TAC_HD void grp_fwd1(int t, int job, int lev, const DecompFast& dc, const uint32_t* __restrict__ dig, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+TAC_HD void grp_fwd1(int t, int job, int lev, const DecompFast& dc, const uint32_t* __restrict__ dig, cplx* __restrict__ S) {
     const uint32_t* d = dig + ((size_t)job * (C::L - 1) + (lev - 1)) * C::M;
-    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, wT, S + (size_t)job * C::M);
+    fft_fwd_pass1<C::N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, S + (size_t)job * C::M);
 }
 template <class C>
-TAC_HD void grp_fwd2(int t, int job, cplx* __restrict__ S) { fft_fwd_pass2<C::N>(t, S + (size_t)job * C::M); }
+TAC_HD void grp_fwd2(int t, int job, const cplx* __restrict__ wT, cplx* __restrict__ S) { fft_fwd_pass2<C::N>(t, wT, S + (size_t)job * C::M); }
 // out[b][c] += Σ_p fft(digits_{lev,p} of ct b) · GGSW[lev-1][p][c]   at the slots owned by this thread.
 // ggsw: Fourier GGSW of this step, [L][G][G][M] slot-ordered (already scaled by 2^-64 / M).
 // Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that
@@ -160,23 +159,27 @@ TAC_HD void grp_inv2(int t, int job, const cplx* __restrict__ S, uint64_t* __res
 
 // Fourier transform of a torus polynomial (keys): 16 threads, buffer S[M]; result left in S in slot order, scaled by `scale`·2^-64.
 template <int N>
-TAC_HD void key_fft_pass1(int t, const uint64_t* __restrict__ poly, double scale, const cplx* __restrict__ wT, cplx* __restrict__ S) {
+TAC_HD void key_fft_pass1(int t, const uint64_t* __restrict__ poly, double scale, cplx* __restrict__ S) {
     fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) {
         a = torus_to_f64(poly[jj]) * scale;
         b = torus_to_f64(poly[jj + N / 2]) * scale;
-    }, wT, S);
+    }, S);
 }
 
-// host-side construction of the combined table in extended precision (capi.cu and the CPU emulation)
+// host-side construction of the twiddle tables (tab_len(N) entries, layout in ep_core.cuh) in extended precision
 inline void build_wT(int N, cplx* wT) {
     const int M = N / 2, P = M / 16;
     const long double pi = 3.141592653589793238462643383279502884L;
-    for (int q = 0; q < P; q++)
-        for (int t = 0; t < 16; t++) {
-            const long double ang = pi * t / N - 2.0L * pi * (long double)(t * q) / M;
-            cplx w; w.x = (double)cosl(ang); w.y = (double)sinl(ang);
-            wT[slot_of(q, t)] = w;
-        }
+    for (int i = 0; i < tab_len(N); i++) wT[i] = mk(0.0, 0.0);
+    for (int q = 0; q < P; q++) {
+        const long double rho = pi / N - 2.0L * pi * (long double)q / M;           // arg ρ_q
+        for (int t = 0; t < 16; t++) wT[slot_of(q, t)] = mk((double)cosl(rho * t), (double)sinl(rho * t));
+        for (int len = 2; len <= 16; len *= 2)
+            for (int k = 0; k < len / 2; k++) {
+                const long double ang = rho * (16 / len) - 2.0L * pi * (long double)k / len;
+                wT[M + (len / 2 - 1 + k) * P + q] = mk((double)cosl(ang), (double)sinl(ang));
+            }
+    }
 }
 
 }  // namespace tac

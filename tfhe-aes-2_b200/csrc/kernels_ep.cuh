@@ -17,13 +17,13 @@ poly_fft_kernel(const uint64_t* __restrict__ polys, size_t npoly, double scale, 
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* S = reinterpret_cast<cplx*>(smem_raw);
     cplx* wT = S + 16 * M;
-    for (int i = threadIdx.x; i < M; i += 256) wT[i] = g_wT[i];
+    for (int i = threadIdx.x; i < tab_len(N); i += 256) wT[i] = g_wT[i];
     __syncthreads();
     const int grp = threadIdx.x >> 4, t = threadIdx.x & 15;
     const size_t poly = (size_t)blockIdx.x * 16 + grp;
-    if (poly < npoly) key_fft_pass1<N>(t, polys + poly * N, scale, wT, S + grp * M);
+    if (poly < npoly) key_fft_pass1<N>(t, polys + poly * N, scale, S + grp * M);
     __syncthreads();
-    if (poly < npoly) fft_fwd_pass2<N>(t, S + grp * M);
+    if (poly < npoly) fft_fwd_pass2<N>(t, wT, S + grp * M);
     __syncthreads();
     const size_t base = (size_t)blockIdx.x * 16 * M;
     const size_t lim = npoly * M;
@@ -40,9 +40,9 @@ struct EpSmem {
         S = reinterpret_cast<cplx*>(acc + C::acc_words);
         dig = reinterpret_cast<uint32_t*>(S + C::s_cplx);
         wT = reinterpret_cast<cplx*>(dig + C::dig_words);
-        extra = reinterpret_cast<unsigned char*>(wT + C::M);
+        extra = reinterpret_cast<unsigned char*>(wT + tab_len(C::N));
     }
-    static constexpr size_t bytes = C::acc_words * 8 + C::s_cplx * 16 + C::dig_words * 4 + (size_t)C::M * 16;
+    static constexpr size_t bytes = C::acc_words * 8 + C::s_cplx * 16 + C::dig_words * 4 + (size_t)tab_len(C::N) * 16;
 };
 
 // one step on the operand whose coefficients jj and jj + N/2 of polynomial `job` are given by coef(job, jj, x0, x1); the
@@ -77,7 +77,7 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
 #ifdef TAC_EP_TIMING
     long long tac_tprev = clock64();
 #endif
-    if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { coef(job, jj, x0, x1); }, dc, sm.dig, sm.wT, sm.S);
+    if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { coef(job, jj, x0, x1); }, dc, sm.dig, sm.S);
     if (active && !DO_FWD && DO_DEC) {          // decomposition alone
         for (int m = 0; m < C::M / 16; m++) {
             uint32_t w[C::L];
@@ -89,11 +89,19 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
             sm.S[(size_t)job * C::M + t + 16 * m].x = (double)w[C::L - 1];
         }
     }
-    if (active && DO_FWD && !DO_DEC) grp_fwd1<C>(t, job, 1, dc, sm.dig, sm.wT, sm.S);
+    if (active && DO_FWD && !DO_DEC) grp_fwd1<C>(t, job, 1, dc, sm.dig, sm.S);
     TAC_EP_T(0);
-    if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);                 // in flight during pass 2 and the barrier
+    // The first key rows are requested AFTER pass 2 (in flight during the barrier only): pass 2 holds 16 values and 15
+    // twiddles, and a ring that is live across it costs registers the FFT needs (measured with the FMA-fused passes:
+    // 112.4 ms late vs 121.8 ms early for 6144 ciphertexts).  TAC_PREFETCH_EARLY restores the old order (tools/pbs_bench.cu).
+#ifdef TAC_PREFETCH_EARLY
+    if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
+#endif
     __syncwarp();
-    if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
+    if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, sm.S);
+#ifndef TAC_PREFETCH_EARLY
+    if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
+#endif
     TAC_EP_T(1);
     __syncthreads();
     TAC_EP_T(2);
@@ -104,11 +112,16 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     TAC_EP_T(4);
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
-        if (active && DO_FWD) grp_fwd1<C>(t, job, lev, dc, sm.dig, sm.wT, sm.S);
+        if (active && DO_FWD) grp_fwd1<C>(t, job, lev, dc, sm.dig, sm.S);
         TAC_EP_T(5);
+#ifdef TAC_PREFETCH_EARLY
         if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
+#endif
         __syncwarp();
-        if (active && DO_FWD) grp_fwd2<C>(t, job, sm.S);
+        if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, sm.S);
+#ifndef TAC_PREFETCH_EARLY
+        if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
+#endif
         TAC_EP_T(6);
         __syncthreads();
         TAC_EP_T(7);
@@ -135,6 +148,17 @@ __device__ __forceinline__ uint64_t sample_extract_elem(const uint64_t* __restri
     return (j == 0) ? a[0] : (0ull - a[C::N - j]);
 }
 
+// stand-alone form of the sample extraction the PBS / vertical-packing kernels fuse (parity test entry point)
+template <int N, int K>
+__global__ void sample_extract_kernel(const uint64_t* __restrict__ glwe, size_t n_glwe, uint64_t* __restrict__ out) {
+    typedef EpCfg<N, K, 1, 1> C;
+    constexpr size_t LW = (size_t)K * N + 1;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n_glwe * LW; idx += (size_t)gridDim.x * blockDim.x) {
+        const size_t g = idx / LW;
+        out[idx] = sample_extract_elem<C>(glwe + g * C::G * N, (int)(idx - g * LW));
+    }
+}
+
 // ================================================================================================ PBS (homomorphic_shift_boolean)
 // in: small LWE [nct][n+1]; out: big LWE [nct][kN+1] encrypting bit·2·alpha.
 // [U] wop_pbs.rs::homomorphic_shift_boolean + bootstrap.rs::{blind_rotate_assign, bootstrap}
@@ -158,7 +182,7 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
         if (i == n) a += (1ull << 62);                             // centre the error for the negacyclic LUT
         return modswitch(a, LogN<N>::v);
     };
-    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int i = tid; i < tab_len(C::N); i += NT) sm.wT[i] = g_wT[i];
     if (tid < B) { rot_sm[tid] = switched(tid, 0); rot_sm[B + tid] = switched(tid, n); }
     __syncthreads();
     // accumulator = trivial GLWE(-alpha in every coefficient) · X^{-b~}
@@ -221,7 +245,7 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
     cplx* S = reinterpret_cast<cplx*>(acc + C::acc_words);                     // [L][JOBS][M]   (storage index s ↔ level s+1)
     uint32_t* dig = reinterpret_cast<uint32_t*>(S + (size_t)L * C::s_cplx);    // [JOBS][L][M]
     cplx* wT = reinterpret_cast<cplx*>(dig + (size_t)JOBS * L * C::M);
-    int* rot_sm = reinterpret_cast<int*>(wT + C::M);                           // [2][B]
+    int* rot_sm = reinterpret_cast<int*>(wT + tab_len(C::N));                  // [2][B]
     const int tid = threadIdx.x;
     const int grp = tid >> 4, t = tid & 15;
     const int part = grp / JOBS, job = grp - part * JOBS;                      // part: share of the pairs in P0, level index in P1
@@ -235,7 +259,7 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
         if (i == n) a += (1ull << 62);
         return modswitch(a, LogN<N>::v);
     };
-    for (int i = tid; i < C::M; i += NT) wT[i] = g_wT[i];
+    for (int i = tid; i < tab_len(C::N); i += NT) wT[i] = g_wT[i];
     if (tid < B) { rot_sm[tid] = switched(tid, 0); rot_sm[B + tid] = switched(tid, n); }
     __syncthreads();
     for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
@@ -277,17 +301,25 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
         __syncthreads();
         // ---- P1: forward FFT of level part+1 of polynomial job; the MAC threads request their first key rows
         cplx g[MAC_DEPTH][C::G];
+#ifndef TAC_WIDE_PREFETCH_LATE
         if (tid < NMAC) {
 #pragma unroll
             for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, NMAC>(row_ptr(ggsw, r), 0, tid, g[r]);
         }
+#endif
         {
             const uint32_t* d = dig + ((size_t)job * L + part) * C::M;
             cplx* Sj = S + ((size_t)part * JOBS + job) * C::M;
-            if (active) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, wT, Sj);
+            if (active) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, Sj);
             __syncwarp();                          // outside the predicate: a warp may hold one active and one idle group
-            if (active) fft_fwd_pass2<N>(t, Sj);
+            if (active) fft_fwd_pass2<N>(t, wT, Sj);
         }
+#ifdef TAC_WIDE_PREFETCH_LATE
+        if (tid < NMAC) {
+#pragma unroll
+            for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, NMAC>(row_ptr(ggsw, r), 0, tid, g[r]);
+        }
+#endif
         __syncthreads();
         // ---- P2: Fourier MAC over all L·G key rows
         if (tid < NMAC) {
@@ -331,7 +363,7 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
     }
 }
 template <class C> struct WideSmem {
-    static constexpr size_t bytes = C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)C::M * 16 + 2 * C::B * sizeof(int) + 16;
+    static constexpr size_t bytes = C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)tab_len(C::N) * 16 + 2 * C::B * sizeof(int) + 16;
 };
 
 // ================================================================================================ vertical packing
@@ -348,7 +380,7 @@ vp_kernel(const cplx* __restrict__ ggsw_f, int n_in, int first_ggsw, const uint6
     EpSmem<C> sm(smem_raw);
     const int tid = threadIdx.x;
     const int box = blockIdx.y, o0 = blockIdx.x * B;
-    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int i = tid; i < tab_len(C::N); i += NT) sm.wT[i] = g_wT[i];
     for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
         const int b = idx / (C::G * N), rem = idx - b * C::G * N, p = rem / N, j = rem - p * N;
         const int o = o0 + b;
@@ -402,7 +434,7 @@ cmux_tree_kernel(const cplx* __restrict__ ggsw_f, int n_in, int ggsw_idx, const 
     const int tid = threadIdx.x;
     const int pair = blockIdx.x, o = blockIdx.y, box = blockIdx.z;
     const int n_pairs = n_nodes_in / 2;
-    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int i = tid; i < tab_len(C::N); i += NT) sm.wT[i] = g_wT[i];
     for (int idx = tid; idx < C::G * N; idx += NT) {
         uint64_t c0, c1;
         if (node_in) {

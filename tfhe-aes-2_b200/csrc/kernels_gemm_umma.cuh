@@ -276,9 +276,14 @@ lwe_gemm_umma_kernel(const uint8_t* __restrict__ DA, int nct, int mtiles, const 
 }
 
 // ---- patch for digits d' == 2^16 (digit = +B/2, exact ties only): out[ct][j][:] −= 2^16 · key[j][k][:]
+// umma_digit_tiles_kernel lists the (ciphertext, k) positions it zeroed.  The list has a fixed capacity; when a batch holds
+// more ties than that (crafted or trivial inputs — random ciphertexts produce ≈ 2^-16 per digit), the list is ignored
+// altogether and pfks_fixup_scan_kernel recomputes the digits and patches every tie, so no input can produce a silently
+// wrong GGSW.  Both kernels are always launched; each begins by reading the counter and one of them returns at once.
 __global__ void pfks_fixup_kernel(const uint32_t* __restrict__ fix_count, const uint2* __restrict__ fix_list, uint32_t fix_cap,
                                   const uint64_t* __restrict__ key, int Kd, int W, int nkeys, uint64_t* __restrict__ out) {
-    const uint32_t n = min(*fix_count, fix_cap);
+    const uint32_t n = *fix_count;
+    if (n > fix_cap) return;                         // overflow: pfks_fixup_scan_kernel does the whole job
     for (uint32_t e = blockIdx.x; e < n; e += gridDim.x) {
         const uint2 f = fix_list[e];
         for (int idx = threadIdx.x; idx < nkeys * W; idx += blockDim.x) {
@@ -287,6 +292,27 @@ __global__ void pfks_fixup_kernel(const uint32_t* __restrict__ fix_count, const 
             atomicAdd(reinterpret_cast<unsigned long long*>(out + ((size_t)f.x * nkeys + j) * W + col), (unsigned long long)(0ull - v));
         }
     }
+}
+// grid (column tiles of 256, nct): every thread re-derives the digits of its ciphertext (cheap) and subtracts the key rows of
+// the ties from its own column — no atomics, no capacity
+__global__ void __launch_bounds__(256)
+pfks_fixup_scan_kernel(const uint32_t* __restrict__ fix_count, uint32_t fix_cap, const uint64_t* __restrict__ in, int in_stride, int b, int l,
+                       const uint64_t* __restrict__ key, int Kd, int W, int nkeys, uint64_t* __restrict__ out) {
+    if (*fix_count <= fix_cap) return;
+    const int ct = blockIdx.y;
+    const int idx = blockIdx.x * 256 + threadIdx.x;
+    if (idx >= nkeys * W) return;
+    const int j = idx / W, col = idx - j * W;
+    uint64_t acc = 0;
+    const int n_el = Kd / l;
+    for (int i = 0; i < n_el; i++) {
+        uint64_t st = decomp_init_state(closest_representable(in[(size_t)ct * in_stride + i], b, l), b, l);
+        for (int lev = l; lev >= 1; lev--) {
+            const int64_t d = decomp_next(st, b);
+            if (d == (int64_t)(1u << (b - 1))) acc += key[((size_t)j * Kd + (size_t)i * l + (lev - 1)) * W + col] << 16;
+        }
+    }
+    out[((size_t)ct * nkeys + j) * W + col] -= acc;
 }
 
 }  // namespace tac

@@ -3,6 +3,7 @@
 #include "kernels_ep.cuh"
 #include "shape_launch.h"
 
+#include <algorithm>
 #include <cstdlib>
 
 namespace tac {
@@ -18,7 +19,7 @@ constexpr int SN = TAC_N, SK = TAC_K;
 
 cudaError_t s_poly_fft(const KLaunch& k, const uint64_t* polys, size_t npoly, double scale, double2* out) {
     constexpr int M = SN / 2;
-    const size_t smem = (size_t)(16 * M + M) * sizeof(cplx);
+    const size_t smem = (size_t)(16 * M + tab_len(SN)) * sizeof(cplx);
     TAC_SET_SMEM(poly_fft_kernel<SN>, smem);
     poly_fft_kernel<SN><<<(unsigned)((npoly + 15) / 16), 256, smem, k.stream>>>(polys, npoly, scale, k.wT, out);
     return cudaGetLastError();
@@ -50,7 +51,7 @@ cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, 
     //    — the latency configuration for small batches (one AES block = 128 ciphertexts).
     const long waves3 = ((nct + 2) / 3 + k.sm_count - 1) / k.sm_count, waves1 = (nct + k.sm_count - 1) / k.sm_count;
     if (L >= 2 && waves1 * 39 <= waves3 * 86) return launch_pbs_wide<(L >= 2 ? L : 2), 3>(k, small, nct, n, bsk, base_log, alpha, out);
-    return launch_pbs<L, 3, 256, 1, 5>(k, small, nct, n, bsk, base_log, alpha, out);
+    return launch_pbs<L, 3, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation
 #endif
@@ -104,7 +105,7 @@ cmux_rotate_test_kernel(const cplx* __restrict__ ggsw_f, const int* __restrict__
     EpSmem<C> sm(smem_raw);
     const int tid = threadIdx.x;
     uint64_t* g = acc_io + (size_t)blockIdx.x * C::G * SN;
-    for (int i = tid; i < C::M; i += NT) sm.wT[i] = g_wT[i];
+    for (int i = tid; i < tab_len(C::N); i += NT) sm.wT[i] = g_wT[i];
     for (int i = tid; i < C::G * SN; i += NT) sm.acc[i] = g[i];
     __syncthreads();
     cplx outr[MC::SPT][1][C::G];
@@ -133,7 +134,14 @@ cudaError_t s_cmux_test(const KLaunch& k, int levels, const double2* gf, const i
     return cudaErrorInvalidValue;
 }
 
-const ShapeOps kOps = {SN, SK, s_poly_fft, s_pbs, s_vp, s_tree, s_cmux_test};
+cudaError_t s_sample_extract(const KLaunch& k, const uint64_t* glwe, size_t n, uint64_t* out) {
+    const size_t total = n * ((size_t)SK * SN + 1);
+    const unsigned grid = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)k.sm_count * 16);
+    sample_extract_kernel<SN, SK><<<grid ? grid : 1, 256, 0, k.stream>>>(glwe, n, out);
+    return cudaGetLastError();
+}
+
+const ShapeOps kOps = {SN, SK, s_poly_fft, s_pbs, s_vp, s_tree, s_cmux_test, s_sample_extract};
 
 }  // namespace
 

@@ -28,6 +28,8 @@ struct ShapeOps {
                         const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out);
     // one CMux-with-rotation step per accumulator (test entry point)
     cudaError_t (*cmux_test)(const KLaunch&, int levels, const double2* ggsw_f, const int* rot, int base_log, int n_acc, uint64_t* acc);
+    // GLWE [n][(k+1)N] → LWE [n][kN+1], coefficient 0 (test entry point of the fused sample extraction)
+    cudaError_t (*sample_extract)(const KLaunch&, const uint64_t* glwe, size_t n, uint64_t* out);
 };
 
 const ShapeOps* shape_ops_n512_k4();

@@ -125,10 +125,10 @@ int main(int argc, char** argv) {
     std::vector<cplx> bsk(bsk_n);
     std::uniform_real_distribution<double> ud(-0.05, 0.05);
     for (auto& v : bsk) { v.x = ud(rng); v.y = ud(rng); }
-    std::vector<cplx> wT(M); build_wT(N, wT.data());
+    std::vector<cplx> wT(tab_len(N)); build_wT(N, wT.data());
     CK(cudaMalloc(&b.small, small.size() * 8)); CK(cudaMemcpy(b.small, small.data(), small.size() * 8, cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b.bsk, bsk_n * sizeof(cplx))); CK(cudaMemcpy(b.bsk, bsk.data(), bsk_n * sizeof(cplx), cudaMemcpyHostToDevice));
-    CK(cudaMalloc(&b.wT, M * sizeof(cplx))); CK(cudaMemcpy(b.wT, wT.data(), M * sizeof(cplx), cudaMemcpyHostToDevice));
+    CK(cudaMalloc(&b.wT, wT.size() * sizeof(cplx))); CK(cudaMemcpy(b.wT, wT.data(), wT.size() * sizeof(cplx), cudaMemcpyHostToDevice));
     CK(cudaMalloc(&b.out, (size_t)b.nct * (K * N + 1) * 8));
     CK(cudaMalloc(&b.sum, 8));
     {   // DFMA peak
@@ -147,7 +147,10 @@ int main(int argc, char** argv) {
     int v = 0;
 #define V(B_, NT_, MINB_, D_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_>("B=" #B_ " NT=" #NT_ " minb=" #MINB_ " depth=" #D_, b); v++;
 #define VW(B_, NT_, D_) if (mask & (1u << v)) run_wide<B_, NT_, D_>("wide B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
-#include "pbs_bench_variants.inc"
+#ifndef TAC_VARIANTS
+#define TAC_VARIANTS "pbs_bench_variants.inc"
+#endif
+#include TAC_VARIANTS
 #undef V
 #undef VW
     return 0;

@@ -91,6 +91,18 @@ int tac_client_encrypt_bits(tac_client_key* ck, const uint8_t* bits, size_t n, u
 int tac_client_decrypt_bits(tac_client_key* ck, const uint64_t* cts, size_t n, uint8_t* bits);
 int tac_client_decrypt_phases(tac_client_key* ck, const uint64_t* cts, size_t n, uint64_t* phases);
 
+/* ------------------------------------------------------------------ wire format (csrc/wire.cpp documents the layout) */
+/* Flat little-endian dump of the raw `u64` containers the reference obtains from tfhe-rs with into_raw_parts /
+ * as_ref() (shortint_woppbs_1bit.rs:245-268): a file written by a tfhe-rs process (INTEGRATION.md has the Rust writer)
+ * loads here and vice versa.  Any key pointer may be NULL (section omitted / not read); lengths are tac_key_len(). */
+int tac_keys_save(const char* path, const tac_params* p, const uint64_t* sk_glwe, const uint64_t* sk_lwe, const uint64_t* bsk_std,
+                  const uint64_t* ksk, const uint64_t* pfpksk);
+int tac_keys_load_params(const char* path, tac_params* p, uint32_t* present_mask /* bit i: section id i present */);
+int tac_keys_load(const char* path, const tac_params* p, uint64_t* sk_glwe, uint64_t* sk_lwe, uint64_t* bsk_std, uint64_t* ksk, uint64_t* pfpksk);
+/* LweCiphertextListOwned<u64>: [count][lwe_size] words.  Load with words == NULL queries the sizes. */
+int tac_lwe_list_save(const char* path, uint64_t lwe_size, uint64_t count, const uint64_t* words);
+int tac_lwe_list_load(const char* path, uint64_t* lwe_size, uint64_t* count, uint64_t* words, size_t capacity_words);
+
 /* ------------------------------------------------------------------ server context (one per GPU) */
 tac_ctx* tac_ctx_create(const tac_params* p, int device);   /* NULL if there is no usable CUDA device */
 void tac_ctx_destroy(tac_ctx* ctx);
@@ -101,6 +113,7 @@ int tac_ctx_sm_count(tac_ctx* ctx);
 /* Evaluation keys (FheContext's server_key + wopbs_key — shortint_woppbs_1bit.rs:166-172).  The BSK is taken in the
  * STANDARD domain and converted on the device. */
 int tac_ctx_upload_keys(tac_ctx* ctx, const uint64_t* bsk_std, const uint64_t* ksk, const uint64_t* pfpksk);
+int tac_ctx_load_keys(tac_ctx* ctx, const char* key_file);    /* evaluation keys from a tac_keys_save / tfhe-rs-written file */
 /* Multi-GPU replication: non-root ranks allocate, every rank exposes its device buffers (which: 0 Fourier BSK, 1 KSK,
  * 2 PFPKSK) to the caller's collective (torch.distributed / ncclBroadcast), then marks them valid. */
 int tac_ctx_alloc_keys(tac_ctx* ctx);

@@ -91,6 +91,56 @@ def test_client_default_seed_is_os_entropy(tac):
     assert set(np.unique(k)) <= {0, 1} and k.size == 677
 
 
+def test_wire_format_round_trip(tac, ck64, tmp_path):
+    """§8 f4: flat dump of the raw tfhe-rs containers — keys and ciphertext lists survive a round trip bit for bit, other
+    parameter sets and corrupted payloads are refused"""
+    import ctypes as C
+    path = str(tmp_path / "keys.tac")
+    ck64.save_keys(path, secret=True)
+    p, present = tac.key_file_info(path)
+    assert present == {1, 2, 3, 4, 5} and p.lwe_dimension == 677 and p.polynomial_size == 512
+    L = tac.load_library()
+    for which, name in enumerate(("sk_glwe", "sk_lwe", "bsk", "ksk", "pfpksk")):
+        out = np.empty(L.tac_key_len(C.byref(p), which), dtype=np.uint64)
+        args = [None] * 5
+        args[which] = out.ctypes.data
+        assert L.tac_keys_load(path.encode(), C.byref(p), *args) == 0
+        assert np.array_equal(out, getattr(ck64, name)), name
+    # header: magic, version, section count, the parameter block
+    raw = open(path, "rb").read(96)
+    assert raw[:8] == b"TACWIRE\x01" and int.from_bytes(raw[8:12], "little") == 1 and int.from_bytes(raw[12:16], "little") == 5
+    assert np.frombuffer(raw[16:64], dtype=np.int32).tolist() == [677, 4, 512, 3, 12, 4, 3, 1, 13, 2, 16, 64]
+    # a client rebuilt from the file decrypts what the original encrypted
+    ck2 = tac.ClientKey.load_secret_keys(path)
+    bits = [1, 0, 0, 1, 1]
+    assert ck2.decrypt_bits(ck64.encrypt_bits(bits, first_index=777)).tolist() == bits
+    assert ck64.decrypt_bits(ck2.encrypt_bits(bits)).tolist() == bits
+    # evaluation-only file: no secret sections
+    pub = str(tmp_path / "eval.tac")
+    ck64.save_keys(pub)
+    assert tac.key_file_info(pub)[1] == {3, 4, 5}
+    with pytest.raises(OSError):
+        tac.ClientKey.load_secret_keys(pub)
+    # wrong parameter set / flipped payload bit are refused
+    other = tac.params_preset(4)
+    out = np.empty(L.tac_key_len(C.byref(other), 1), dtype=np.uint64)
+    assert L.tac_keys_load(path.encode(), C.byref(other), None, out.ctypes.data, None, None, None) != 0
+    blob = bytearray(open(path, "rb").read())
+    blob[96 + 40 + 1000] ^= 0x01                                    # inside the first payload
+    bad = str(tmp_path / "bad.tac")
+    open(bad, "wb").write(blob)
+    out = np.empty(2048, dtype=np.uint64)
+    assert L.tac_keys_load(bad.encode(), C.byref(p), out.ctypes.data, None, None, None, None) != 0
+    # ciphertext lists
+    cts = ck64.encrypt_bytes(b"\x53\xca")
+    lst = str(tmp_path / "cts.tac")
+    tac.save_lwe_list(lst, cts)
+    back = tac.load_lwe_list(lst)
+    assert back.shape == (16, 2049) and np.array_equal(back, cts.reshape(16, 2049))
+    with pytest.raises(OSError):
+        tac.load_lwe_list(path)                                     # a key file is not an LWE list
+
+
 def test_context_rejects_unsupported_parameter_sets(tac):
     """constraints the kernels assume beyond (N, k) are validated up front (before any device is touched)"""
     import ctypes as C

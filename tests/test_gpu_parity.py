@@ -298,6 +298,24 @@ def test_concurrent_callers_on_one_context(gpu64, ol):
     ctx.set_coalescing(window_us=200)
 
 
+def test_keys_and_ciphertexts_through_wire_files(tac, ck64, ol, tmp_path):
+    """§8 f4 on the device: a fresh context takes its evaluation keys from a key file, inputs and outputs travel as LWE
+    list files, and a client rebuilt from the file's secret sections decrypts the result"""
+    kf, cf, of = (str(tmp_path / n) for n in ("keys.tac", "in.tac", "out.tac"))
+    ck64.save_keys(kf, secret=True)
+    ctx = tac.FheContext(tac.key_file_info(kf)[0])
+    ctx.load_keys(kf)
+    tac.save_lwe_list(cf, ck64.encrypt_bytes(b"\x53\x00"))
+    lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    out = ctx.circuit_bootstrap_batch(tac.load_lwe_list(cf).reshape(2, 8, -1), lut)
+    tac.save_lwe_list(of, out)
+    ck2 = tac.ClientKey.load_secret_keys(kf)
+    assert ck2.decrypt_bytes(tac.load_lwe_list(of)) == bytes([ol.sbox(0x53), ol.sbox(0x00)])
+    other = tac.FheContext(4)
+    with pytest.raises(RuntimeError, match="another parameter set"):
+        other.load_keys(kf)
+
+
 def test_wopbs_empty_batch(gpu64, ol):
     ck, ctx = gpu64
     lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))

@@ -70,6 +70,12 @@ _SIGNATURES = {
     "tac_client_encrypt_bits": (C.c_int, [C.c_void_p, _u8p, C.c_size_t, C.c_uint64, _u64p]),
     "tac_client_decrypt_bits": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u8p]),
     "tac_client_decrypt_phases": (C.c_int, [C.c_void_p, _u64p, C.c_size_t, _u64p]),
+    "tac_keys_save": (C.c_int, [C.c_char_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tac_keys_load_params": (C.c_int, [C.c_char_p, C.POINTER(Params), C.POINTER(C.c_uint32)]),
+    "tac_keys_load": (C.c_int, [C.c_char_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "tac_lwe_list_save": (C.c_int, [C.c_char_p, C.c_uint64, C.c_uint64, C.c_void_p]),
+    "tac_lwe_list_load": (C.c_int, [C.c_char_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.c_void_p, C.c_size_t]),
+    "tac_ctx_load_keys": (C.c_int, [C.c_void_p, C.c_char_p]),
     "tac_ctx_create": (C.c_void_p, [C.POINTER(Params), C.c_int]),
     "tac_ctx_destroy": (None, [C.c_void_p]),
     "tac_last_error": (C.c_char_p, [C.c_void_p]),
@@ -175,6 +181,33 @@ def generate_multivariate_luts(input_bits, output_bits, polynomial_size, f):
     return out
 
 
+def save_lwe_list(path, cts):
+    """LweCiphertextListOwned<u64> as a wire file: cts is [count][lwe_size] (any leading shape is flattened)"""
+    a = np.ascontiguousarray(cts, dtype=np.uint64)
+    a = a.reshape(-1, a.shape[-1])
+    if load_library().tac_lwe_list_save(os.fsencode(path), a.shape[1], a.shape[0], a.ctypes.data) != 0:
+        raise OSError(f"cannot write {path}")
+
+
+def load_lwe_list(path):
+    L = load_library()
+    size, count = C.c_uint64(), C.c_uint64()
+    if L.tac_lwe_list_load(os.fsencode(path), C.byref(size), C.byref(count), None, 0) != 0:
+        raise OSError(f"{path}: not an LWE list file")
+    out = np.empty((count.value, size.value), dtype=np.uint64)
+    if L.tac_lwe_list_load(os.fsencode(path), None, None, out.ctypes.data, out.size) != 0:
+        raise OSError(f"{path}: truncated or corrupted")
+    return out
+
+
+def key_file_info(path):
+    """(Params, set of section ids) of a key file"""
+    p, mask = Params(), C.c_uint32()
+    if load_library().tac_keys_load_params(os.fsencode(path), C.byref(p), C.byref(mask)) != 0:
+        raise OSError(f"{path}: not a key file")
+    return p, {i for i in range(32) if mask.value >> i & 1}
+
+
 class LookupTable:
     """WopbsLUTBase plus its shape; registered on the device on first use."""
 
@@ -250,6 +283,26 @@ class ClientKey:
     bsk = property(lambda self: self._key(2))
     ksk = property(lambda self: self._key(3))
     pfpksk = property(lambda self: self._key(4))
+
+    # -- wire format (csrc/wire.cpp): the raw tfhe-rs containers, so keys can come from / go to a reference build
+    def save_keys(self, path, secret=False, evaluation=True):
+        ptr = lambda which, on: self._key(which).ctypes.data if on else None
+        rc = self.L.tac_keys_save(os.fsencode(path), C.byref(self.params), ptr(0, secret), ptr(1, secret), ptr(2, evaluation), ptr(3, evaluation),
+                                  ptr(4, evaluation))
+        if rc != 0:
+            raise OSError(f"cannot write {path}")
+
+    @classmethod
+    def load_secret_keys(cls, path):
+        """a client around the secret keys of a key file (sections 1 and 2); encryption randomness is fresh OS entropy"""
+        p, present = key_file_info(path)
+        if not {1, 2} <= present:
+            raise OSError(f"{path} holds no secret keys")
+        L = load_library()
+        g, l = np.empty(L.tac_key_len(C.byref(p), 0), dtype=np.uint64), np.empty(L.tac_key_len(C.byref(p), 1), dtype=np.uint64)
+        if L.tac_keys_load(os.fsencode(path), C.byref(p), g.ctypes.data, l.ctypes.data, None, None, None) != 0:
+            raise OSError(f"{path}: truncated or corrupted")
+        return cls(p, secret_keys=(g, l))
 
     # -- raw array API
     def encrypt_bits(self, bits, first_index=None):
@@ -424,6 +477,10 @@ class FheContext(NoiseContext):
     def upload_keys(self, client_key):
         bsk, ksk, pf = client_key.bsk, client_key.ksk, client_key.pfpksk
         self._check(self.L.tac_ctx_upload_keys(self.h, bsk.ctypes.data, ksk.ctypes.data, pf.ctypes.data))
+
+    def load_keys(self, path):
+        """evaluation keys from a wire file written by ClientKey.save_keys or by a tfhe-rs process"""
+        self._check(self.L.tac_ctx_load_keys(self.h, os.fsencode(path)))
 
     def alloc_keys(self):
         self._check(self.L.tac_ctx_alloc_keys(self.h))

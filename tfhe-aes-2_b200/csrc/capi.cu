@@ -12,6 +12,7 @@
 #include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <string>
 #include <vector>
@@ -84,6 +85,7 @@ struct tac_ctx {
     int aes_lut24 = -1, aes_lut8 = -1, aes_lut1 = -1;
     // AES key schedule
     uint64_t* key_sched = nullptr;
+    uint64_t* rc_rows = nullptr;     // trivial(RC[1..10]) as byte ciphertexts [10][8][kN+1], uploaded once
     // workspace
     DevBuf ws_in, ws_out, ws_small, ws_ksdig, ws_pbs, ws_pfdig, ws_ggsw, ws_ggswf, ws_tree_a, ws_tree_b, ws_state, ws_muls, ws_misc;
     size_t max_cts = 16384;
@@ -405,7 +407,7 @@ void tac_ctx_destroy(tac_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     for (void* p : {(void*)ctx->bsk_f, (void*)ctx->ksk, (void*)ctx->pfpksk, (void*)ctx->ks_corr, (void*)ctx->pfks_corr, (void*)ctx->pfks_planes, (void*)ctx->ks_planes, (void*)ctx->pfks_fix, (void*)ctx->wT,
-                    (void*)ctx->key_sched})
+                    (void*)ctx->key_sched, (void*)ctx->rc_rows})
         if (p) cudaFree(p);
     for (auto& l : ctx->luts) cudaFree(l.dev);
     for (DevBuf* b : {&ctx->ws_in, &ctx->ws_out, &ctx->ws_small, &ctx->ws_ksdig, &ctx->ws_pbs, &ctx->ws_pfdig, &ctx->ws_ggsw, &ctx->ws_ggswf,
@@ -552,6 +554,19 @@ int tac_ctx_upload_keys(tac_ctx* ctx, const uint64_t* bsk_std, const uint64_t* k
         CU(cudaStreamSynchronize(ctx->stream));
     }
     return tac_ctx_keys_ready(ctx);
+}
+
+// evaluation keys straight from a key file (wire.cpp): sections 3-5 must be present and belong to this parameter set
+int tac_ctx_load_keys(tac_ctx* ctx, const char* path) {
+    LOCK(ctx);
+    tac_params fp;
+    uint32_t present = 0;
+    if (int rc = tac_keys_load_params(path, &fp, &present)) return fail(ctx, rc, std::string("cannot read key file ") + (path ? path : "(null)"));
+    if (memcmp(&fp, &ctx->p, sizeof fp) != 0) return fail(ctx, TAC_ERR_ARG, "key file was written for another parameter set");
+    if ((present & 0x38u) != 0x38u) return fail(ctx, TAC_ERR_STATE, "key file lacks evaluation-key sections (3 BSK, 4 KSK, 5 PFPKSK)");
+    std::vector<uint64_t> bsk(tac_key_len(&fp, 2)), ksk(tac_key_len(&fp, 3)), pf(tac_key_len(&fp, 4));
+    if (int rc = tac_keys_load(path, &fp, nullptr, nullptr, bsk.data(), ksk.data(), pf.data())) return fail(ctx, rc, "key file truncated or corrupted (checksum)");
+    return tac_ctx_upload_keys(ctx, bsk.data(), ksk.data(), pf.data());
 }
 
 int tac_lut_register(tac_ctx* ctx, int n_in, int n_out, const uint64_t* table, size_t len) {
@@ -780,10 +795,17 @@ int tac_aes_key_schedule(tac_ctx* ctx, const uint64_t* key_bits_host, uint64_t* 
     uint64_t* sub = rot + word;
     uint64_t* acc = sub + word;
     CU(cudaMemcpyAsync(ek, key_bits_host, 4 * word * 8, cudaMemcpyHostToDevice, ctx->stream));
-    // trivial(RC) constants: body += encode_bit(1) on the set bits of RC[i/4], byte 0 (:154; Byte::trivial data_model.rs:35-43)
-    static const uint8_t RC[11] = {0x00, 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36};
-    std::vector<uint64_t> rcv(byte);
-    TRY(ensure(ctx, ctx->ws_misc, byte * 8));
+    // trivial(RC) constants: body += encode_bit(1) on the set bits of RC[i/4], byte 0 (:154; Byte::trivial data_model.rs:35-43).
+    // All ten rows are uploaded once per context, so the 40 steps below enqueue without a host synchronisation.
+    if (!ctx->rc_rows) {
+        static const uint8_t RC[11] = {0x00, 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36};
+        std::vector<uint64_t> rows((size_t)10 * byte, 0ull);
+        for (int r = 1; r <= 10; r++)
+            for (int bit = 0; bit < 8; bit++)
+                if (RC[r] & (0x80 >> bit)) rows[(size_t)(r - 1) * byte + (size_t)bit * L + (L - 1)] = tac_encode_bit(1);
+        CU(cudaMalloc(&ctx->rc_rows, rows.size() * 8));
+        CU(cudaMemcpy(ctx->rc_rows, rows.data(), rows.size() * 8, cudaMemcpyHostToDevice));
+    }
     for (int i = 4; i < 44; i++) {
         uint64_t* cur = ek + (size_t)i * word;
         const uint64_t* prev = ek + (size_t)(i - 1) * word;
@@ -793,12 +815,7 @@ int tac_aes_key_schedule(tac_ctx* ctx, const uint64_t* key_bits_host, uint64_t* 
             CU(cudaMemcpyAsync(rot, prev + byte, 3 * byte * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             CU(cudaMemcpyAsync(rot + 3 * byte, prev, byte * 8, cudaMemcpyDeviceToDevice, ctx->stream));
             TRY(wopbs_dev(ctx, ctx->luts[ctx->aes_lut8], 4, rot, sub));                                       // sub_word
-            std::fill(rcv.begin(), rcv.end(), 0ull);
-            for (int bit = 0; bit < 8; bit++)
-                if (RC[i / 4] & (0x80 >> bit)) rcv[(size_t)bit * L + (L - 1)] = tac_encode_bit(1);
-            CU(cudaMemcpyAsync(ctx->ws_misc.p, rcv.data(), byte * 8, cudaMemcpyHostToDevice, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
-            TRY(tac_lwe_add_batch_dev(ctx, sub, ctx->ws_misc.as<uint64_t>(), 8));
+            TRY(tac_lwe_add_batch_dev(ctx, sub, ctx->rc_rows + (size_t)(i / 4 - 1) * byte, 8));
             addend = sub;
         }
         CU(cudaMemcpyAsync(acc, ek + (size_t)(i - 4) * word, word * 8, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -243,6 +243,35 @@ TAC_HD void fft_fwd_pass1(int t, Src src, cplx* __restrict__ S) {
     static_for<0, P>([&](auto qc) { constexpr int q = decltype(qc)::value; S[slot_of(q, t)] = v[q]; });
 }
 // ------------------------------------------------------------------------------------------------ forward, pass 2 (in place)
+// The 15 butterfly twiddles of lane q do not depend on the data: a caller can fetch them into registers BEFORE pass 1
+// (fft_fwd_twiddles), so that those shared-memory reads overlap the FP64 work of pass 1 instead of lengthening the load
+// burst at the start of pass 2 — every group of a CTA runs the same pass at the same time, so a pass is a burst of loads,
+// then arithmetic, then a burst of stores, and the load/store unit idles exactly while the FP64 pipe is busy.
+// (Only when a thread runs one DFT-16 in pass 2, i.e. N = 512; larger N load them inside the pass.)
+#ifndef TAC_FWD_TW_PREFETCH
+#define TAC_FWD_TW_PREFETCH 0
+#endif
+#ifndef TAC_INV_TW_EARLY
+#define TAC_INV_TW_EARLY 0
+#endif
+template <int N> struct FwdTw { static constexpr bool PRE = TAC_FWD_TW_PREFETCH && (N / 32 == 16); static constexpr int LEN = PRE ? 15 : 1; };
+template <int N>
+TAC_HD void fft_fwd_twiddles(int t, const cplx* __restrict__ wT, cplx (&tw)[FwdTw<N>::LEN]) {
+    if constexpr (FwdTw<N>::PRE) {
+        constexpr int M = N / 2, P = M / 16;
+        static_for<0, 15>([&](auto ec) { constexpr int e = decltype(ec)::value; tw[e] = wT[M + e * P + t]; });
+    }
+}
+template <int N, class TwFn>
+TAC_HD void fft_fwd_pass2_core(int q, TwFn&& twf, cplx* __restrict__ S) {
+    cplx v[16];
+    static_for<0, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; v[bitrev<16>(tt)] = S[slot_of(q, tt)]; });
+    dit_stages<16, 2>(v, [&](auto lc, auto kc, cplx& u, cplx& w) {
+        constexpr int LEN = decltype(lc)::value, k = decltype(kc)::value;
+        bfly_r(u, w, twf(std::integral_constant<int, LEN / 2 - 1 + k>{}));
+    });
+    static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; S[slot_of(q, r)] = v[r]; });
+}
 template <int N>
 TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int M = N / 2, P = M / 16;
@@ -250,16 +279,17 @@ TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, cplx* __restrict__
 #pragma unroll
     for (int c2 = 0; c2 < P / 16; c2++) {
         const int q = t + 16 * c2;
-        cplx v[16];
-        static_for<0, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; v[bitrev<16>(tt)] = S[slot_of(q, tt)]; });
-        dit_stages<16, 2>(v, [&](auto lc, auto kc, cplx& u, cplx& w) {
-            constexpr int LEN = decltype(lc)::value, k = decltype(kc)::value;
-            bfly_r(u, w, wF[(LEN / 2 - 1 + k) * P + q]);
-        });
-        static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; S[slot_of(q, r)] = v[r]; });
+        fft_fwd_pass2_core<N>(q, [&](auto ec) { return wF[decltype(ec)::value * P + q]; }, S);
     }
 }
+// pass 2 with the twiddles already in registers (fft_fwd_twiddles)
+template <int N>
+TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, const cplx (&tw)[FwdTw<N>::LEN], cplx* __restrict__ S) {
+    if constexpr (FwdTw<N>::PRE) fft_fwd_pass2_core<N>(t, [&](auto ec) { return tw[decltype(ec)::value]; }, S);
+    else fft_fwd_pass2<N>(t, wT, S);
+}
 // ------------------------------------------------------------------------------------------------ inverse, pass A (in place)
+// the 16 twiddles are requested together with the data, ahead of the arithmetic (same reasoning as above)
 template <int N>
 TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int M = N / 2, P = M / 16;
@@ -268,8 +298,16 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
         const int q = t + 16 * c2;
         cplx v[16];
         static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; v[bitrev<16>(r)] = S[slot_of(q, r)]; });
+#if TAC_INV_TW_EARLY
+        cplx w[16];
+        static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; w[tt] = wT[slot_of(q, tt)]; });
+        dft_inv<16>(v);
+        S[slot_of(q, 0)] = v[0];
+        static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; S[slot_of(q, tt)] = cmul_conj(v[tt], w[tt]); });
+#else
         dft_inv<16>(v);
         twiddle_store_conj<16>(v, [&](int tt) { return slot_of(q, tt); }, wT, S);
+#endif
     }
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass B

@@ -89,6 +89,10 @@ TAC_HD void grp_fwd1(int t, int job, int lev, const DecompFast& dc, const uint32
 }
 template <class C>
 TAC_HD void grp_fwd2(int t, int job, const cplx* __restrict__ wT, cplx* __restrict__ S) { fft_fwd_pass2<C::N>(t, wT, S + (size_t)job * C::M); }
+template <class C>
+TAC_HD void grp_fwd2(int t, int job, const cplx* __restrict__ wT, const cplx (&tw)[FwdTw<C::N>::LEN], cplx* __restrict__ S) {
+    fft_fwd_pass2<C::N>(t, wT, tw, S + (size_t)job * C::M);
+}
 // out[b][c] += Σ_p fft(digits_{lev,p} of ct b) · GGSW[lev-1][p][c]   at the slots owned by this thread.
 // ggsw: Fourier GGSW of this step, [L][G][G][M] slot-ordered (already scaled by 2^-64 / M).
 // Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that

@@ -77,6 +77,8 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
 #ifdef TAC_EP_TIMING
     long long tac_tprev = clock64();
 #endif
+    cplx tw[FwdTw<C::N>::LEN];          // pass-2 twiddles of this lane, fetched ahead of pass 1 (ep_core.cuh)
+    if (active && DO_FWD) fft_fwd_twiddles<C::N>(t, sm.wT, tw);
     if (active && DO_FWD && DO_DEC) grp_decomp_fwd1<C>(t, job, [&](int jj, uint64_t& x0, uint64_t& x1) { coef(job, jj, x0, x1); }, dc, sm.dig, sm.S);
     if (active && !DO_FWD && DO_DEC) {          // decomposition alone
         for (int m = 0; m < C::M / 16; m++) {
@@ -98,7 +100,7 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
 #endif
     __syncwarp();
-    if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, sm.S);
+    if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, tw, sm.S);
 #ifndef TAC_PREFETCH_EARLY
     if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
 #endif
@@ -112,13 +114,14 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     TAC_EP_T(4);
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
+        if (active && DO_FWD) fft_fwd_twiddles<C::N>(t, sm.wT, tw);
         if (active && DO_FWD) grp_fwd1<C>(t, job, lev, dc, sm.dig, sm.S);
         TAC_EP_T(5);
 #ifdef TAC_PREFETCH_EARLY
         if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
 #endif
         __syncwarp();
-        if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, sm.S);
+        if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, tw, sm.S);
 #ifndef TAC_PREFETCH_EARLY
         if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
 #endif
@@ -310,9 +313,11 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
         {
             const uint32_t* d = dig + ((size_t)job * L + part) * C::M;
             cplx* Sj = S + ((size_t)part * JOBS + job) * C::M;
+            cplx tw[FwdTw<N>::LEN];
+            if (active) fft_fwd_twiddles<N>(t, wT, tw);
             if (active) fft_fwd_pass1<N>(t, [&](int jj, double& a, double& b) { unpack_digits(d[jj], dc, a, b); }, Sj);
             __syncwarp();                          // outside the predicate: a warp may hold one active and one idle group
-            if (active) fft_fwd_pass2<N>(t, wT, Sj);
+            if (active) fft_fwd_pass2<N>(t, wT, tw, Sj);
         }
 #ifdef TAC_WIDE_PREFETCH_LATE
         if (tid < NMAC) {

@@ -17,7 +17,8 @@ template <class F> static bool panics_with(F f, const char* what) {
 }
 
 int main() {
-    auto keys = generate_keys(64, 424242);
+    const uint64_t seed = 424242;
+    auto keys = generate_keys(64, &seed);
     auto& ck = keys.first; auto& ctx = keys.second;
     // test_bit_encrypt_decrypt / test_bit_xor
     BitCt b1 = ck.encrypt(0, ctx), b2 = ck.encrypt(1, ctx), b3 = ck.encrypt(0, ctx), b4 = ck.encrypt(1, ctx);

@@ -1,5 +1,6 @@
 // tfhe_aes_cli — the reference's binary (src/bin/main.rs) on the B200 path:
 //   tfhe_aes_cli --key 76b8e0ada0f13d90405d6ae55386bd28 --iv bdd219b8a08ded1a --number-of-outputs 10 [--generic] [--seed S]
+// (--seed is for tests: without it the keys come from OS entropy, like the reference's)
 // --generic runs the reference's generic per-byte code path (fhe_sbox_gal_mul_pbs over ByteT) instead of the fused device path.
 #include "tfhe_aes.hpp"
 
@@ -34,10 +35,12 @@ int main(int argc, char** argv) {
     if (kv.size() != 16) { fprintf(stderr, "invalid key length, must be 16 bytes\n"); return 2; }
     if (iv.size() != 8) { fprintf(stderr, "invalid iv length, must be 8 bytes\n"); return 2; }
     const size_t n_out = std::stoul(a["--number-of-outputs"]);
-    const uint64_t seed = a.count("--seed") ? std::stoull(a["--seed"]) : 0;
+    // keys come from OS entropy; --seed S (TEST ONLY) makes them reproducible and therefore publicly computable
+    const bool have_seed = a.count("--seed") != 0;
+    const uint64_t seed = have_seed ? std::stoull(a["--seed"]) : 0;
     printf("using implementation: CudaWoppbs1bit (%s path)\n", generic ? "generic per-byte" : "fused device");
     try {
-        auto keys = tfhe::cuda_woppbs_1bit::generate_keys(64, seed);                           // generate_keys_sqrd_lvl_64 (main.rs:82-83)
+        auto keys = tfhe::cuda_woppbs_1bit::generate_keys(64, have_seed ? &seed : nullptr);                           // generate_keys_sqrd_lvl_64 (main.rs:82-83)
         auto& client_key = keys.first; auto& ctx = keys.second;
         Key key_clear; std::copy(kv.begin(), kv.end(), key_clear.begin());
         // client side: FHE encrypt AES key and blocks (main.rs:107-116)

@@ -74,6 +74,14 @@ public:
         if (tac_generate_lut(input_bits, output_bits, parameters.polynomial_size, tab.data(), lut.data()) != TAC_OK) throw Panic("generate_lookup_table: bad arguments");
         return {std::move(lut), {input_bits, output_bits}};
     }
+    // the reference keeps one `static OnceLock` per LUT (fhe_impls/shortint_woppbs_1bit.rs:49,54,85,90,97) because it has one
+    // parameter set per process; here a LUT belongs to the context that built it (another context may have another N)
+    const LookupTable& cached_lut(int kind, int input_bits, int output_bits, const std::function<uint64_t(uint16_t)>& f) const {
+        std::lock_guard<std::mutex> g(*mu_);
+        auto it = named_luts_->find(kind);
+        if (it == named_luts_->end()) it = named_luts_->emplace(kind, generate_lookup_table(input_bits, output_bits, f)).first;
+        return it->second;
+    }
     int lut_id(const LookupTable& lut) const {
         std::lock_guard<std::mutex> g(*mu_);
         auto it = lut_ids_->find(lut.first.data());
@@ -88,6 +96,7 @@ private:
     std::shared_ptr<std::atomic<uint64_t>> ct_counter_ = std::make_shared<std::atomic<uint64_t>>(0);
     std::shared_ptr<std::mutex> mu_ = std::make_shared<std::mutex>();
     std::shared_ptr<std::map<const uint64_t*, int>> lut_ids_ = std::make_shared<std::map<const uint64_t*, int>>();
+    std::shared_ptr<std::map<int, LookupTable>> named_luts_ = std::make_shared<std::map<int, LookupTable>>();
 };
 
 // :28-32, :86-122
@@ -137,7 +146,11 @@ inline std::vector<BitCt> circuit_bootstrap(const FheContext& ctx, const std::ve
 // :189-226
 class ClientKey {
 public:
-    ClientKey(const tac_params& p, uint64_t seed) : p_(p), ck_(tac_client_keygen(&p, seed), tac_client_free) {}
+    // seed == nullptr: 256 bits of OS entropy, like the reference (engine.rs:164-168); a seed gives reproducible — hence
+    // publicly computable — keys and is for tests only
+    ClientKey(const tac_params& p, const uint64_t* seed) : p_(p), ck_(seed ? tac_client_keygen(&p, *seed) : tac_client_keygen_os(&p), tac_client_free) {
+        if (!ck_) throw Panic("client key generation failed (no OS entropy source)");
+    }
     void gen_eval_keys(int threads = 0) { tac_client_gen_eval_keys(ck_.get(), threads); }
     void upload(const FheContext& ctx) {
         gen_eval_keys();
@@ -163,7 +176,7 @@ private:
 };
 
 // FheContext::generate_keys_sqrd_lvl_{1,4,64,256} :229-243
-inline std::pair<ClientKey, FheContext> generate_keys(int preset, uint64_t seed, int device = 0) {
+inline std::pair<ClientKey, FheContext> generate_keys(int preset, const uint64_t* seed = nullptr, int device = 0) {
     tac_params p;
     if (tac_params_preset(preset, &p) != TAC_OK) throw Panic("unknown parameter preset");
     ClientKey ck(p, seed);
@@ -311,13 +324,12 @@ using Byte = data_model::Byte<BitCt>;
 
 struct ByteT {
     static const FheContext& ctx_of(const Byte& b) { return *b[0].context; }
-    static const LookupTable& identity_lut(const FheContext& c) { static LookupTable l = c.generate_lookup_table(1, 1, [](uint16_t b) { return (uint64_t)b; }); return l; }
-    static const LookupTable& sbox_lut(const FheContext& c) { static LookupTable l = c.generate_lookup_table(8, 8, [](uint16_t b) { return (uint64_t)SBOX[b]; }); return l; }
+    static const LookupTable& identity_lut(const FheContext& c) { return c.cached_lut(0, 1, 1, [](uint16_t b) { return (uint64_t)b; }); }
+    static const LookupTable& sbox_lut(const FheContext& c) { return c.cached_lut(1, 8, 8, [](uint16_t b) { return (uint64_t)SBOX[b]; }); }
     static const LookupTable& sbox_gal_mul_lut(const FheContext& c) {                                               // :97-111
-        static LookupTable l = c.generate_lookup_table(8, 24, [](uint16_t b) {
+        return c.cached_lut(2, 8, 24, [](uint16_t b) {
             return ((uint64_t)gf_256_mul(SBOX[b], 1) << 16) | ((uint64_t)gf_256_mul(SBOX[b], 2) << 8) | (uint64_t)gf_256_mul(SBOX[b], 3);
         });
-        return l;
     }
     static void bootstrap_assign(Byte& self) {                                                                      // :18-30 (8 one-bit boots, batched)
         const FheContext& c = ctx_of(self);

@@ -23,7 +23,7 @@ def main():
     ap.add_argument("--iv", required=True)
     ap.add_argument("--key", required=True)
     ap.add_argument("--implementation", default="cuda-woppbs-1bit", choices=["cuda-woppbs-1bit"])
-    ap.add_argument("--seed", type=int, default=0, help="seed of the FHE key / noise streams (the reference seeds from the OS)")
+    ap.add_argument("--seed", type=int, default=None, help="TEST ONLY: reproducible (publicly computable) keys; default = OS entropy like the reference")
     ap.add_argument("--device", type=int, default=0)
     args = ap.parse_args()
     print(f"using implementation: {args.implementation}")

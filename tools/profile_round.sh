@@ -6,7 +6,7 @@
 TAG=${1:-r1}
 BLOCKS=${2:-48}
 cd "$(dirname "$0")/.."
-CMD="python bench.py --steps 1 --warmup 1 --blocks $BLOCKS --no-cpu-baseline"
+CMD="python bench.py --steps 1 --warmup 1 --blocks $BLOCKS --no-cpu-baseline --no-key-expansion"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv $CMD > gpurun_out/ncu_launches_$TAG.log 2>&1
 SKIP=$(python - <<PY
 import csv

@@ -272,6 +272,23 @@ TAC_HD void fft_fwd_pass2_core(int q, TwFn&& twf, cplx* __restrict__ S) {
     });
     static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; S[slot_of(q, r)] = v[r]; });
 }
+// multiply by exp(2πi·A/128), A a compile-time angle (free for multiples of a quarter turn)
+template <int A>
+TAC_HD cplx rot128(cplx d) {
+    constexpr int a = ((A % 128) + 128) % 128;
+    if constexpr (a == 0) return d;
+    else if constexpr (a == 32) return mk(-d.y, d.x);
+    else if constexpr (a == 64) return mk(-d.x, -d.y);
+    else if constexpr (a == 96) return mk(d.y, -d.x);
+    else { const double c = cosq<a>(), sn = sinq<a>(); return mk(fma(-d.y, sn, d.x * c), fma(d.y, c, d.x * sn)); }
+}
+#ifndef TAC_TW_DERIVE
+#define TAC_TW_DERIVE 1
+#endif
+// TAC_TW_DERIVE: the 15 twiddles of pass 2 are  ρ_q^{16/LEN} · e^{-2πi k/LEN}.  Only the four powers ρ_q^{8,4,2,1} (the
+// k = 0 entries) are read from the table; the others are formed with a compile-time rotation — 8 complex multiplies per
+// pass instead of 11 more 16-byte shared-memory loads per thread.  The kernel's load/store unit is its busiest resource
+// (63 % of the data-pipe wavefronts) while the FP64 pipe has slack (46 %), so arithmetic is the cheaper currency.
 template <int N>
 TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int M = N / 2, P = M / 16;
@@ -279,7 +296,17 @@ TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, cplx* __restrict__
 #pragma unroll
     for (int c2 = 0; c2 < P / 16; c2++) {
         const int q = t + 16 * c2;
+#if TAC_TW_DERIVE
+        cplx base[4];                      // LEN = 2, 4, 8, 16 at k = 0: table entries 0, 1, 3, 7
+        static_for<0, 4>([&](auto ic) { constexpr int i = decltype(ic)::value; base[i] = wF[((1 << i) - 1) * P + q]; });
+        fft_fwd_pass2_core<N>(q, [&](auto ec) {
+            constexpr int e = decltype(ec)::value;
+            constexpr int lg = (e >= 7) ? 3 : (e >= 3) ? 2 : (e >= 1) ? 1 : 0, LEN = 2 << lg, k = e - (LEN / 2 - 1);
+            return rot128<-128 * k / LEN>(base[lg]);
+        }, S);
+#else
         fft_fwd_pass2_core<N>(q, [&](auto ec) { return wF[decltype(ec)::value * P + q]; }, S);
+#endif
     }
 }
 // pass 2 with the twiddles already in registers (fft_fwd_twiddles)
@@ -298,7 +325,16 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
         const int q = t + 16 * c2;
         cplx v[16];
         static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; v[bitrev<16>(r)] = S[slot_of(q, r)]; });
-#if TAC_INV_TW_EARLY
+#if TAC_TW_DERIVE
+        // ρ_q^t for t = 1, 2, 4, 8 from the table, the other powers as products (at most three multiplications deep)
+        cplx w[16];
+        w[1] = wT[slot_of(q, 1)]; w[2] = wT[slot_of(q, 2)]; w[4] = wT[slot_of(q, 4)]; w[8] = wT[slot_of(q, 8)];
+        dft_inv<16>(v);
+        w[3] = cmul(w[2], w[1]); w[5] = cmul(w[4], w[1]); w[6] = cmul(w[4], w[2]); w[7] = cmul(w[4], w[3]);
+        static_for<9, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; w[tt] = cmul(w[8], w[tt - 8]); });
+        S[slot_of(q, 0)] = v[0];
+        static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; S[slot_of(q, tt)] = cmul_conj(v[tt], w[tt]); });
+#elif TAC_INV_TW_EARLY
         cplx w[16];
         static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; w[tt] = wT[slot_of(q, tt)]; });
         dft_inv<16>(v);

@@ -12,6 +12,8 @@
 #include <vector>
 #include <random>
 #include "kernels_ep.cuh"
+#include "experiments/kernels_park.cuh"
+#include "experiments/kernels_wide512.cuh"
 
 using namespace tac;
 
@@ -112,6 +114,67 @@ void run_wide(const char* name, const Bufs& b) {
     fflush(stdout);
 }
 
+template <int B, int NT, int DEPTH, bool SPLIT>
+void run_park(const char* name, const Bufs& b) {
+    typedef EpCfg<N, K, L, B> C;
+    const size_t smem = ParkSmem<C>::bytes;
+    auto kern = pbs_park_kernel<N, K, L, B, NT, DEPTH, SPLIT>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
+    const unsigned grid = (b.nct + B - 1) / B;
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMemset(b.out, 0, (size_t)b.nct * (K * N + 1) * 8));
+    kern<<<grid, NT, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f, tot = 0;
+    for (int r = 0; r < b.reps; r++) {
+        CK(cudaEventRecord(e0));
+        kern<<<grid, NT, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best; tot += ms;
+    }
+    CK(cudaMemset(b.sum, 0, 8));
+    checksum_kernel<<<256, 256>>>(b.out, (size_t)b.nct * (K * N + 1), b.sum);
+    unsigned long long h; CK(cudaMemcpy(&h, b.sum, 8, cudaMemcpyDeviceToHost));
+    const double flop = (double)b.nct * n_lwe * 389120.0;
+    printf("%-28s regs=%3d lmem=%4zu smem=%6zu occ=%d  best %8.3f ms  avg %8.3f ms  %6.2f TF/s  frac %.3f  %7.1f PBS/ms  sum=%016llx\n", name, fa.numRegs,
+           (size_t)fa.localSizeBytes, smem, occ, best, tot / b.reps, flop / (best * 1e-3) / 1e12, flop / (best * 1e-3) / 1e12 / b.peak, b.nct / best, h);
+    fflush(stdout);
+}
+
+template <int DEPTH>
+void run_wide512(const char* name, const Bufs& b) {
+    typedef EpCfg<N, K, L, 1> C;
+    const size_t smem = WideSmem<C>::bytes;
+    auto kern = pbs_wide512_kernel<N, K, L, DEPTH>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 512, smem));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMemset(b.out, 0, (size_t)b.nct * (K * N + 1) * 8));
+    kern<<<b.nct, 512, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f, tot = 0;
+    for (int r = 0; r < b.reps; r++) {
+        CK(cudaEventRecord(e0));
+        kern<<<b.nct, 512, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best; tot += ms;
+    }
+    CK(cudaMemset(b.sum, 0, 8));
+    checksum_kernel<<<256, 256>>>(b.out, (size_t)b.nct * (K * N + 1), b.sum);
+    unsigned long long h; CK(cudaMemcpy(&h, b.sum, 8, cudaMemcpyDeviceToHost));
+    const double flop = (double)b.nct * n_lwe * 389120.0;
+    printf("%-28s regs=%3d lmem=%4zu smem=%6zu occ=%d  best %8.3f ms  avg %8.3f ms  %6.2f TF/s  frac %.3f  %7.1f PBS/ms  sum=%016llx\n", name, fa.numRegs,
+           (size_t)fa.localSizeBytes, smem, occ, best, tot / b.reps, flop / (best * 1e-3) / 1e12, flop / (best * 1e-3) / 1e12 / b.peak, b.nct / best, h);
+    fflush(stdout);
+}
+
 int main(int argc, char** argv) {
     Bufs b;
     b.nct = argc > 1 ? atoi(argv[1]) : 6144;
@@ -147,11 +210,17 @@ int main(int argc, char** argv) {
     int v = 0;
 #define V(B_, NT_, MINB_, D_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_>("B=" #B_ " NT=" #NT_ " minb=" #MINB_ " depth=" #D_, b); v++;
 #define VW(B_, NT_, D_) if (mask & (1u << v)) run_wide<B_, NT_, D_>("wide B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
+#define VP(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, false>("park B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
+#define VW5(D_) if (mask & (1u << v)) run_wide512<D_>("wide512 depth=" #D_, b); v++;
+#define VS(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, true>("park/split B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #ifndef TAC_VARIANTS
 #define TAC_VARIANTS "pbs_bench_variants.inc"
 #endif
 #include TAC_VARIANTS
 #undef V
 #undef VW
+#undef VP
+#undef VS
+#undef VW5
     return 0;
 }

@@ -98,14 +98,22 @@ TAC_HD void grp_fwd2(int t, int job, const cplx* __restrict__ wT, const cplx (&t
 // Key prefetch ring of the MAC: rows 0..MAC_DEPTH-1 of this thread's first slot are requested BEFORE the barrier that
 // precedes the MAC (the L2 latency hides behind the barrier wait), row p+MAC_DEPTH is requested while row p is multiplied.
 // MAC_DEPTH is a kernel template parameter (register budget: each ring entry is G complex values).
+// TAC_DBG_KEY_ONE_ROW (development only, tools/pbs_bench.cu): every key load hits the same 20 KB row, which stays in L1 —
+// times the kernel WITHOUT its L2 → SM key stream (results are then meaningless).
 template <class C, int NT_MAC>
 TAC_HD void mac_load_row(const cplx* __restrict__ gl, int p, int tau, cplx (&dst)[C::G]) {
+#ifdef TAC_DBG_KEY_ONE_ROW
+    p = 0;
+#endif
 #pragma unroll
     for (int c = 0; c < C::G; c++) dst[c] = TAC_LDG(gl + (size_t)(p * C::G + c) * C::M + tau);
 }
 template <class C, int NT_MAC, int MAC_DEPTH>
 TAC_HD void ph_mac_prefetch(int tid, int lev, const cplx* __restrict__ ggsw, cplx (&g)[MAC_DEPTH][C::G]) {
     if (tid >= NT_MAC) return;
+#ifdef TAC_DBG_KEY_ONE_ROW
+    lev = 1;
+#endif
     const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
 #pragma unroll
     for (int p = 0; p < MAC_DEPTH && p < C::G; p++) mac_load_row<C, NT_MAC>(gl, p, tid, g[p]);
@@ -114,6 +122,9 @@ template <class C, int NT_MAC, int SPT, int MAC_DEPTH>
 TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* __restrict__ S, cplx (&out)[SPT][C::B][C::G],
                    cplx (&g)[MAC_DEPTH][C::G]) {
     if (tid >= NT_MAC) return;
+#ifdef TAC_DBG_KEY_ONE_ROW
+    lev = 1;
+#endif
     const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
 #pragma unroll
     for (int it = 0; it < SPT; it++) {
@@ -131,6 +142,35 @@ TAC_HD void ph_mac(int tid, int lev, const cplx* __restrict__ ggsw, const cplx* 
                 for (int c = 0; c < C::G; c++) cfma(out[it][b][c], x, g[p % MAC_DEPTH][c]);
             }
             if (p + MAC_DEPTH < C::G) mac_load_row<C, NT_MAC>(gl, p + MAC_DEPTH, tau, g[p % MAC_DEPTH]);
+        }
+    }
+}
+// MAC with the first NS key rows of the level STAGED in shared memory (kst: [NS][G][M], filled by a bulk asynchronous copy
+// while the forward transforms ran) and the remaining rows in the register ring, all of them requested before the barrier:
+// nothing is fetched from L2 while the MAC runs.  Rows are still consumed in the order 0 … G-1, so the sums are the same words.
+template <class C, int NT_MAC, int MAC_DEPTH, int NS>
+TAC_HD void ph_mac_prefetch_staged(int tid, int lev, const cplx* __restrict__ ggsw, cplx (&g)[MAC_DEPTH][C::G]) {
+    static_assert(NS + MAC_DEPTH >= C::G, "every row that is not staged must fit the ring");
+    if (tid >= NT_MAC) return;
+    const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
+#pragma unroll
+    for (int p = NS; p < C::G; p++) mac_load_row<C, NT_MAC>(gl, p, tid, g[p - NS]);
+}
+template <class C, int NT_MAC, int MAC_DEPTH, int NS>
+TAC_HD void ph_mac_staged(int tid, const cplx* __restrict__ kst, const cplx* __restrict__ S, cplx (&out)[1][C::B][C::G], cplx (&g)[MAC_DEPTH][C::G]) {
+    if (tid >= NT_MAC) return;
+#pragma unroll
+    for (int p = 0; p < C::G; p++) {
+        cplx row[C::G];
+        if (p < NS) {
+#pragma unroll
+            for (int c = 0; c < C::G; c++) row[c] = kst[(size_t)(p * C::G + c) * C::M + tid];
+        }
+#pragma unroll
+        for (int b = 0; b < C::B; b++) {
+            const cplx x = S[(size_t)(b * C::G + p) * C::M + tid];
+#pragma unroll
+            for (int c = 0; c < C::G; c++) cfma(out[0][b][c], x, p < NS ? row[c] : g[p < NS ? 0 : p - NS][c]);
         }
     }
 }

@@ -61,9 +61,51 @@ __device__ long long tac_ep_times[32];
 #else
 #define TAC_EP_T(k) do { } while (0)
 #endif
-template <class C, int NT, int MAC_DEPTH = 5, class CoefFn>
+// ---- key staging: the first NS rows of a level's Fourier GGSW travel into shared memory by one bulk asynchronous copy
+// (cp.async.bulk, completion on an mbarrier) issued a whole FFT phase ahead of the MAC that consumes them
+namespace kstage {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+}  // namespace kstage
+template <class C, int NS>
+struct KeyStage {
+    cplx* buf;                   // [NS][G][M]
+    uint32_t bar;                // shared-memory address of the mbarrier
+    uint32_t uses;               // completed waits (parity of the next one)
+    static constexpr uint32_t row_bytes = (uint32_t)(C::G * C::M * sizeof(cplx));
+    static constexpr size_t bytes = (size_t)NS * row_bytes;
+    // one thread: request rows 0 … NS-1 of level `lev` of `ggsw`
+    __device__ __forceinline__ void request(const cplx* __restrict__ ggsw, int lev) const {
+        const cplx* gl = ggsw + (size_t)(lev - 1) * C::G * C::G * C::M;
+        kstage::mbar_expect_tx(bar, NS * row_bytes);
+#pragma unroll
+        for (int r = 0; r < NS; r++) kstage::bulk_g2s(kstage::smem_u32(buf) + r * row_bytes, gl + (size_t)r * C::G * C::M, row_bytes, bar);
+    }
+    __device__ __forceinline__ void wait() { kstage::mbar_wait(bar, uses & 1u); uses++; }
+};
+template <class C> struct KeyStage<C, 0> { static constexpr size_t bytes = 0; };
+// dynamic shared memory of pbs_kernel: the EP buffers, 64 bytes for the rotation degrees and the mbarrier, the staged rows
+template <class C, int NS> struct PbsSmem { static constexpr size_t bytes = EpSmem<C>::bytes + 64 + KeyStage<C, NS>::bytes; };
+
+template <class C, int NT, int MAC_DEPTH = 5, int NS = 0, class CoefFn>
 __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, const cplx* __restrict__ ggsw, CoefFn coef, int base_log,
-                                               cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G]) {
+                                               cplx (&out)[MacCfg<C, NT>::SPT][C::B][C::G], KeyStage<C, NS>* stage = nullptr,
+                                               const cplx* __restrict__ ggsw_next = nullptr) {
     typedef MacCfg<C, NT> MC;
     static_assert(NT / 16 >= C::JOBS, "one 16-thread group per operand polynomial");
     constexpr bool DO_MAC = !(TAC_EP_DBG & 1), DO_FWD = !(TAC_EP_DBG & 2), DO_INV = !(TAC_EP_DBG & 4), DO_DEC = !(TAC_EP_DBG & 8);
@@ -102,15 +144,22 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
     __syncwarp();
     if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, tw, sm.S);
 #ifndef TAC_PREFETCH_EARLY
-    if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
+    if constexpr (NS > 0) { if (DO_MAC) ph_mac_prefetch_staged<C, MC::NT_MAC, MAC_DEPTH, NS>(tid, C::L, ggsw, g); }
+    else if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, C::L, ggsw, g);
 #endif
     TAC_EP_T(1);
     __syncthreads();
     TAC_EP_T(2);
-    if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, C::L, ggsw, sm.S, out, g);
+    if constexpr (NS > 0) {
+        stage->wait();
+        if (DO_MAC) ph_mac_staged<C, MC::NT_MAC, MAC_DEPTH, NS>(tid, stage->buf, sm.S, out, g);
+    } else if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, C::L, ggsw, sm.S, out, g);
     if (C::L == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);         // own slots only: no barrier needed in between
     TAC_EP_T(3);
     __syncthreads();
+    if constexpr (NS > 0) {                 // the staging buffer is free again: rows of the next level (or of the next step)
+        if (tid == 0) { if (C::L > 1) stage->request(ggsw, C::L - 1); else if (ggsw_next) stage->request(ggsw_next, C::L); }
+    }
     TAC_EP_T(4);
 #pragma unroll
     for (int lev = C::L - 1; lev >= 1; lev--) {
@@ -123,15 +172,22 @@ __device__ __forceinline__ void ep_step_device(int tid, const EpSmem<C>& sm, con
         __syncwarp();
         if (active && DO_FWD) grp_fwd2<C>(t, job, sm.wT, tw, sm.S);
 #ifndef TAC_PREFETCH_EARLY
-        if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
+        if constexpr (NS > 0) { if (DO_MAC) ph_mac_prefetch_staged<C, MC::NT_MAC, MAC_DEPTH, NS>(tid, lev, ggsw, g); }
+        else if (DO_MAC) ph_mac_prefetch<C, MC::NT_MAC, MAC_DEPTH>(tid, lev, ggsw, g);
 #endif
         TAC_EP_T(6);
         __syncthreads();
         TAC_EP_T(7);
-        if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, ggsw, sm.S, out, g);
+        if constexpr (NS > 0) {
+            stage->wait();
+            if (DO_MAC) ph_mac_staged<C, MC::NT_MAC, MAC_DEPTH, NS>(tid, stage->buf, sm.S, out, g);
+        } else if (DO_MAC) ph_mac<C, MC::NT_MAC, MC::SPT, MAC_DEPTH>(tid, lev, ggsw, sm.S, out, g);
         if (lev == 1) ph_outw<C, MC::NT_MAC, MC::SPT>(tid, sm.S, out);
         TAC_EP_T(8);
         __syncthreads();
+        if constexpr (NS > 0) {
+            if (tid == 0) { if (lev > 1) stage->request(ggsw, lev - 1); else if (ggsw_next) stage->request(ggsw_next, C::L); }
+        }
         TAC_EP_T(9);
     }
     if (active && DO_INV) grp_inv1<C>(t, job, sm.wT, sm.S);
@@ -165,7 +221,9 @@ __global__ void sample_extract_kernel(const uint64_t* __restrict__ glwe, size_t 
 // ================================================================================================ PBS (homomorphic_shift_boolean)
 // in: small LWE [nct][n+1]; out: big LWE [nct][kN+1] encrypting bit·2·alpha.
 // [U] wop_pbs.rs::homomorphic_shift_boolean + bootstrap.rs::{blind_rotate_assign, bootstrap}
-template <int N, int K, int L, int B, int NT, int MINB, int MAC_DEPTH = 5>
+// NS > 0: the first NS key rows of every level are staged in shared memory by bulk asynchronous copies (KeyStage); the
+// register ring then holds the remaining G - NS rows, so MAC_DEPTH must be >= G - NS.
+template <int N, int K, int L, int B, int NT, int MINB, int MAC_DEPTH = 5, int NS = 0>
 __global__ void __launch_bounds__(NT, MINB)
 pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
            const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
@@ -176,6 +234,17 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
     int* rot_sm = reinterpret_cast<int*>(sm.extra);               // [2][B] monomial degree of the current / next step
     const int tid = threadIdx.x;
     const int ct0 = blockIdx.x * B;
+    KeyStage<C, NS> stage;
+    if constexpr (NS > 0) {
+        unsigned char* base = sm.extra + 64;                       // rot_sm (<= 32 B), the mbarrier at +32, the rows 16-byte aligned
+        stage.buf = reinterpret_cast<cplx*>(base);
+        stage.bar = kstage::smem_u32(sm.extra + 32);
+        stage.uses = 0;
+        if (tid == 0) {
+            kstage::mbar_init(stage.bar, 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     const int n1 = n + 1;
     // modulus-switched element i of ciphertext b (0 for the padding ciphertexts of the last CTA)
     auto switched = [&](int b, int i) -> int {
@@ -207,12 +276,18 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
 #pragma unroll
             for (int c = 0; c < C::G; c++) out[a][b][c] = mk(0.0, 0.0);
     const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    if constexpr (NS > 0) { if (tid == 0 && n > 0) stage.request(bsk, L); }                    // (after the barrier that published the mbarrier)
     for (int i = 0; i < n; i++) {
         const int* rot = rot_sm + (i & 1) * B;
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
-        ep_step_device<C, NT, MAC_DEPTH>(tid, sm, bsk + ggsw_sz * i,
+#ifdef TAC_DBG_KEY_ONE_ROW
+        const cplx* ggsw_i = bsk;
+#else
+        const cplx* ggsw_i = bsk + ggsw_sz * i;
+#endif
+        ep_step_device<C, NT, MAC_DEPTH, NS>(tid, sm, ggsw_i,
                               [&](int job, int jj, uint64_t& x0, uint64_t& x1) { rot_diff_pair<N>(sm.acc + (size_t)job * N, jj, rot[job / C::G], x0, x1); },
-                              base_log, out);
+                              base_log, out, &stage, i + 1 < n ? ggsw_i + ggsw_sz : nullptr);
     }
     __syncthreads();
     constexpr int LW = K * N + 1;

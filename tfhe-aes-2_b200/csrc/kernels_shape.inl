@@ -25,12 +25,12 @@ cudaError_t s_poly_fft(const KLaunch& k, const uint64_t* polys, size_t npoly, do
     return cudaGetLastError();
 }
 
-template <int L, int B, int NT, int MINB = 1, int DEPTH = 5>
+template <int L, int B, int NT, int MINB = 1, int DEPTH = 5, int NS = 0>
 cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
     typedef EpCfg<SN, SK, L, B> C;
-    const size_t smem = EpSmem<C>::bytes + 2 * B * sizeof(int);
-    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH>), smem);
-    pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    const size_t smem = PbsSmem<C, NS>::bytes;
+    TAC_SET_SMEM((pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH, NS>), smem);
+    pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH, NS><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
 template <int L, int DEPTH>
@@ -51,7 +51,7 @@ cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, 
     //    — the latency configuration for small batches (one AES block = 128 ciphertexts).
     const long waves3 = ((nct + 2) / 3 + k.sm_count - 1) / k.sm_count, waves1 = (nct + k.sm_count - 1) / k.sm_count;
     if (L >= 2 && waves1 * 39 <= waves3 * 86) return launch_pbs_wide<(L >= 2 ? L : 2), 3>(k, small, nct, n, bsk, base_log, alpha, out);
-    return launch_pbs<L, 3, 256, 1, 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    return launch_pbs<L, 3, 256, 1, 4, 1>(k, small, nct, n, bsk, base_log, alpha, out);      // ring of 4 rows + 1 row staged by cp.async.bulk
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation
 #endif

@@ -42,11 +42,11 @@ constexpr int N = 512, K = 4, L = 3, n_lwe = 677, BASE_LOG = 12;
 
 struct Bufs { uint64_t* small; cplx* bsk; cplx* wT; uint64_t* out; unsigned long long* sum; int nct; int reps; double peak; };
 
-template <int B, int NT, int MINB, int DEPTH>
+template <int B, int NT, int MINB, int DEPTH, int NS = 0>
 void run(const char* name, const Bufs& b) {
     typedef EpCfg<N, K, L, B> C;
-    const size_t smem = EpSmem<C>::bytes + 2 * B * sizeof(int);
-    auto kern = pbs_kernel<N, K, L, B, NT, MINB, DEPTH>;
+    const size_t smem = PbsSmem<C, NS>::bytes;
+    auto kern = pbs_kernel<N, K, L, B, NT, MINB, DEPTH, NS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -209,6 +209,7 @@ int main(int argc, char** argv) {
     }
     int v = 0;
 #define V(B_, NT_, MINB_, D_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_>("B=" #B_ " NT=" #NT_ " minb=" #MINB_ " depth=" #D_, b); v++;
+#define VN(B_, NT_, MINB_, D_, NS_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_, NS_>("B=" #B_ " NT=" #NT_ " depth=" #D_ " staged=" #NS_, b); v++;
 #define VW(B_, NT_, D_) if (mask & (1u << v)) run_wide<B_, NT_, D_>("wide B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #define VP(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, false>("park B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #define VW5(D_) if (mask & (1u << v)) run_wide512<D_>("wide512 depth=" #D_, b); v++;
@@ -218,6 +219,7 @@ int main(int argc, char** argv) {
 #endif
 #include TAC_VARIANTS
 #undef V
+#undef VN
 #undef VW
 #undef VP
 #undef VS

@@ -279,8 +279,8 @@ int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
     pfks_fixup_kernel<<<64, 256, 0, ctx->stream>>>(ctx->pfks_fix, reinterpret_cast<const uint2*>(ctx->pfks_fix + 2), ctx->fix_cap, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
     TRY(post_launch(ctx, "pfks_fixup_kernel"));
     // more ties than the list holds (crafted / trivial inputs): this kernel re-derives them all; otherwise it returns at once
-    pfks_fixup_scan_kernel<<<dim3((ctx->G() * W + 255) / 256, nct), 256, 0, ctx->stream>>>(ctx->pfks_fix, ctx->fix_cap, in, big1, p.pfks_b, p.pfks_l, ctx->pfpksk, Kd,
-                                                                                            W, ctx->G(), ggsw);
+    pfks_fixup_scan_kernel<<<dim3((ctx->G() * W + 255) / 256, std::min(nct, 2 * ctx->sm_count)), 256, 0, ctx->stream>>>(
+        ctx->pfks_fix, ctx->fix_cap, in, nct, big1, p.pfks_b, p.pfks_l, ctx->pfpksk, Kd, W, ctx->G(), ggsw);
     return post_launch(ctx, "pfks_fixup_scan_kernel");
 }
 

@@ -310,7 +310,10 @@ pbs_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* _
 //   P1  group (level, job): forward FFT of that level from the cached digits                 ── barrier ──
 //   P2  256 slot threads: out = Σ_{level, p} fft(digits) · BSK row, written to the level-1 buffer   ── barrier ──
 //   P3  group (0, job): inverse FFT + torus accumulate                                        ── barrier ──
-template <int N, int K, int L, int B, int NT, int MAC_DEPTH = 5>
+// NS > 0: the LAST NS key rows of every step are staged in shared memory by bulk asynchronous copies issued at the top of the
+// step — a lone ciphertext per SM spends its MAC waiting for the 307 KB GGSW to stream in from L2 (the same kernel with every key
+// load served from L1 runs 19 % faster), and the digit / FFT phases leave that path idle.
+template <int N, int K, int L, int B, int NT, int MAC_DEPTH = 5, int NS = 0>
 __global__ void __launch_bounds__(NT, 1)
 pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
                 const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
@@ -325,6 +328,15 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
     cplx* wT = reinterpret_cast<cplx*>(dig + (size_t)JOBS * L * C::M);
     int* rot_sm = reinterpret_cast<int*>(wT + tab_len(C::N));                  // [2][B]
     const int tid = threadIdx.x;
+    cplx* kst = reinterpret_cast<cplx*>(reinterpret_cast<unsigned char*>(rot_sm) + 64);      // [NS][G][M] staged rows (16-byte aligned)
+    const uint32_t kbar = kstage::smem_u32(reinterpret_cast<unsigned char*>(rot_sm) + 32);
+    uint32_t kuses = 0;
+    constexpr uint32_t ROW_BYTES = (uint32_t)(C::G * C::M * sizeof(cplx));
+    static_assert(NS <= ROWS - MAC_DEPTH && 2 * B * sizeof(int) <= 32, "staged rows come after the rows of the register ring");
+    if (NS > 0 && tid == 0) {
+        kstage::mbar_init(kbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
     const int grp = tid >> 4, t = tid & 15;
     const int part = grp / JOBS, job = grp - part * JOBS;                      // part: share of the pairs in P0, level index in P1
     const bool active = grp < L * JOBS;
@@ -355,11 +367,24 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
     constexpr int P = C::M / 16;
     const int m0 = part * P / L, m1 = (part + 1) * P / L;                     // this group's share of the P register rows
     // key row r (MAC order: level L first, then L-1, …; polynomial p inside) of the step's GGSW
+#ifdef TAC_DBG_KEY_ONE_ROW
+    auto row_ptr = [&](const cplx* ggsw, int) { return ggsw; };
+#else
     auto row_ptr = [&](const cplx* ggsw, int r) { return ggsw + (size_t)((L - 1 - r / C::G) * C::G + (r % C::G)) * C::G * C::M; };
+#endif
     for (int i = 0; i < n; i++) {
         const int* rot = rot_sm + (i & 1) * B;
+#ifdef TAC_DBG_KEY_ONE_ROW
+        const cplx* ggsw = bsk;
+#else
         const cplx* ggsw = bsk + ggsw_sz * i;
+#endif
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+        if (NS > 0 && tid == 0) {              // rows ROWS-NS … ROWS-1 of this step: in flight during P0 and P1
+            kstage::mbar_expect_tx(kbar, NS * ROW_BYTES);
+#pragma unroll
+            for (int r = 0; r < NS; r++) kstage::bulk_g2s(kstage::smem_u32(kst) + r * ROW_BYTES, row_ptr(ggsw, ROWS - NS + r), ROW_BYTES, kbar);
+        }
         // ---- P0: digits
         if (active) {
             const uint64_t* poly = acc + (size_t)job * N;
@@ -409,7 +434,7 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
 #pragma unroll
                 for (int c = 0; c < C::G; c++) out[b][c] = mk(0.0, 0.0);
 #pragma unroll
-            for (int r = 0; r < ROWS; r++) {
+            for (int r = 0; r < ROWS - NS; r++) {
                 const int s = L - 1 - r / C::G, p = r % C::G;                  // storage index of the level, polynomial
 #pragma unroll
                 for (int b = 0; b < B; b++) {
@@ -417,7 +442,23 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
 #pragma unroll
                     for (int c = 0; c < C::G; c++) cfma(out[b][c], x, g[r % MAC_DEPTH][c]);
                 }
-                if (r + MAC_DEPTH < ROWS) mac_load_row<C, NMAC>(row_ptr(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
+                if (r + MAC_DEPTH < ROWS - NS) mac_load_row<C, NMAC>(row_ptr(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
+            }
+            if constexpr (NS > 0) {            // the staged rows arrived while the digits and the transforms were computed
+                kstage::mbar_wait(kbar, kuses & 1u);
+#pragma unroll
+                for (int r = ROWS - NS; r < ROWS; r++) {
+                    const int s = L - 1 - r / C::G, p = r % C::G;
+                    cplx row[C::G];
+#pragma unroll
+                    for (int c = 0; c < C::G; c++) row[c] = kst[(size_t)((r - (ROWS - NS)) * C::G + c) * C::M + tid];
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const cplx x = S[((size_t)s * JOBS + b * C::G + p) * C::M + tid];
+#pragma unroll
+                        for (int c = 0; c < C::G; c++) cfma(out[b][c], x, row[c]);
+                    }
+                }
             }
             // every thread has finished READING its slot of all buffers only after the barrier; the result goes to rows
             // of buffer 0 at this thread's own slot, which no other thread reads in P2
@@ -426,6 +467,7 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
 #pragma unroll
                 for (int c = 0; c < C::G; c++) S[(size_t)(b * C::G + c) * C::M + tid] = out[b][c];
         }
+        if (NS > 0) kuses++;
         __syncthreads();
         // ---- P3: inverse FFT and accumulate (the groups of part 0)
         if (active && part == 0) grp_inv1<C>(t, job, wT, S);
@@ -442,8 +484,8 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
         out_big[(size_t)ct * LW + e] = v;
     }
 }
-template <class C> struct WideSmem {
-    static constexpr size_t bytes = C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)tab_len(C::N) * 16 + 2 * C::B * sizeof(int) + 16;
+template <class C, int NS = 0> struct WideSmem {
+    static constexpr size_t bytes = 64 + (size_t)NS * C::G * C::M * sizeof(cplx) + C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)tab_len(C::N) * 16 + 2 * C::B * sizeof(int) + 16;
 };
 
 // ================================================================================================ vertical packing

@@ -293,26 +293,27 @@ __global__ void pfks_fixup_kernel(const uint32_t* __restrict__ fix_count, const 
         }
     }
 }
-// grid (column tiles of 256, nct): every thread re-derives the digits of its ciphertext (cheap) and subtracts the key rows of
+// grid (column tiles of 256, a few rows striding over the ciphertexts): every thread re-derives the digits of its ciphertext (cheap) and subtracts the key rows of
 // the ties from its own column — no atomics, no capacity
 __global__ void __launch_bounds__(256)
-pfks_fixup_scan_kernel(const uint32_t* __restrict__ fix_count, uint32_t fix_cap, const uint64_t* __restrict__ in, int in_stride, int b, int l,
+pfks_fixup_scan_kernel(const uint32_t* __restrict__ fix_count, uint32_t fix_cap, const uint64_t* __restrict__ in, int nct, int in_stride, int b, int l,
                        const uint64_t* __restrict__ key, int Kd, int W, int nkeys, uint64_t* __restrict__ out) {
     if (*fix_count <= fix_cap) return;
-    const int ct = blockIdx.y;
     const int idx = blockIdx.x * 256 + threadIdx.x;
     if (idx >= nkeys * W) return;
     const int j = idx / W, col = idx - j * W;
-    uint64_t acc = 0;
     const int n_el = Kd / l;
-    for (int i = 0; i < n_el; i++) {
-        uint64_t st = decomp_init_state(closest_representable(in[(size_t)ct * in_stride + i], b, l), b, l);
-        for (int lev = l; lev >= 1; lev--) {
-            const int64_t d = decomp_next(st, b);
-            if (d == (int64_t)(1u << (b - 1))) acc += key[((size_t)j * Kd + (size_t)i * l + (lev - 1)) * W + col] << 16;
+    for (int ct = blockIdx.y; ct < nct; ct += gridDim.y) {
+        uint64_t acc = 0;
+        for (int i = 0; i < n_el; i++) {
+            uint64_t st = decomp_init_state(closest_representable(in[(size_t)ct * in_stride + i], b, l), b, l);
+            for (int lev = l; lev >= 1; lev--) {
+                const int64_t d = decomp_next(st, b);
+                if (d == (int64_t)(1u << (b - 1))) acc += key[((size_t)j * Kd + (size_t)i * l + (lev - 1)) * W + col] << 16;
+            }
         }
+        out[((size_t)ct * nkeys + j) * W + col] -= acc;
     }
-    out[((size_t)ct * nkeys + j) * W + col] -= acc;
 }
 
 }  // namespace tac

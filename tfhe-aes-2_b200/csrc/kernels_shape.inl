@@ -33,12 +33,12 @@ cudaError_t launch_pbs(const KLaunch& k, const uint64_t* small, int nct, int n, 
     pbs_kernel<SN, SK, L, B, NT, MINB, DEPTH, NS><<<(unsigned)((nct + B - 1) / B), NT, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
-template <int L, int DEPTH>
+template <int L, int DEPTH, int NS = 0>
 cudaError_t launch_pbs_wide(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
     typedef EpCfg<SN, SK, L, 1> C;
-    const size_t smem = WideSmem<C>::bytes;
-    TAC_SET_SMEM((pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH>), smem);
-    pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH><<<(unsigned)nct, 256, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    const size_t smem = WideSmem<C, NS>::bytes;
+    TAC_SET_SMEM((pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH, NS>), smem);
+    pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH, NS><<<(unsigned)nct, 256, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
 template <int L>

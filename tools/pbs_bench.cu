@@ -83,11 +83,11 @@ void run(const char* name, const Bufs& b) {
     fflush(stdout);
 }
 
-template <int B, int NT, int DEPTH>
+template <int B, int NT, int DEPTH, int NS = 0>
 void run_wide(const char* name, const Bufs& b) {
     typedef EpCfg<N, K, L, B> C;
-    const size_t smem = WideSmem<C>::bytes;
-    auto kern = pbs_wide_kernel<N, K, L, B, NT, DEPTH>;
+    const size_t smem = WideSmem<C, NS>::bytes;
+    auto kern = pbs_wide_kernel<N, K, L, B, NT, DEPTH, NS>;
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
     int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT, smem));
@@ -211,6 +211,7 @@ int main(int argc, char** argv) {
 #define V(B_, NT_, MINB_, D_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_>("B=" #B_ " NT=" #NT_ " minb=" #MINB_ " depth=" #D_, b); v++;
 #define VN(B_, NT_, MINB_, D_, NS_) if (mask & (1u << v)) run<B_, NT_, MINB_, D_, NS_>("B=" #B_ " NT=" #NT_ " depth=" #D_ " staged=" #NS_, b); v++;
 #define VW(B_, NT_, D_) if (mask & (1u << v)) run_wide<B_, NT_, D_>("wide B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
+#define VWN(B_, NT_, D_, NS_) if (mask & (1u << v)) run_wide<B_, NT_, D_, NS_>("wide B=" #B_ " depth=" #D_ " staged=" #NS_, b); v++;
 #define VP(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, false>("park B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #define VW5(D_) if (mask & (1u << v)) run_wide512<D_>("wide512 depth=" #D_, b); v++;
 #define VS(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, true>("park/split B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
@@ -221,6 +222,7 @@ int main(int argc, char** argv) {
 #undef V
 #undef VN
 #undef VW
+#undef VWN
 #undef VP
 #undef VS
 #undef VW5

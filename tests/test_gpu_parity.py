@@ -218,6 +218,27 @@ def test_vertical_packing_tie_free_all_outputs_tight(gpu64, oracle64, ol):
         assert d.max() < 2.0**42, np.log2(d + 1).round(1).tolist()
 
 
+@pytest.mark.parametrize("n_out", [1, 2, 5])
+def test_vertical_packing_small_output_counts(gpu64, oracle64, n_out):
+    """the vp_kernel instantiations for 1 and 2 outputs per CTA (and a ragged last CTA: 5 = 3 + 2) at phase level, with the
+    tie-free LUT encoding of the test above"""
+    ck, ctx = gpu64
+    tac = __import__("importlib").import_module("tfhe-aes-2_b200")
+    fn = lambda v: (v * 7 + 3) % (1 << n_out)
+    base = ctx.generate_lookup_table(8, n_out, fn).table
+    table = np.where(base != 0, np.uint64(3 << 61), np.uint64(1 << 61)).astype(np.uint64)
+    table[:, 256:] = 0
+    lut = tac.LookupTable(table, 8, n_out)
+    v = 0xB5
+    ggsw = oracle64.pfks(oracle64.pbs(oracle64.keyswitch(ck.encrypt_bytes([v])[0])))[None]
+    got = ctx.stage_vertical_packing(ggsw, lut)[0]
+    ref = oracle64.vertical_packing(ggsw[0], 8, table, n_out)
+    want = [(fn(v) >> (n_out - 1 - o)) & 1 for o in range(n_out)]
+    assert ck.decrypt_bits(got).tolist() == want == ck.decrypt_bits(ref).tolist()
+    d = np.abs(signed(ck.decrypt_phases(got) - ck.decrypt_phases(ref)))
+    assert d.max() < 2.0**42, np.log2(d + 1).round(1).tolist()
+
+
 # ---------------------------------------------------------------------------------------------- the operator, decrypt-checked
 def test_sbox_gal_mul_all_256_bytes(gpu64, ol):
     """BASELINE config 2: the 8-in/24-out SBOX·{1,2,3} WoP-PBS, all byte values in one batch"""

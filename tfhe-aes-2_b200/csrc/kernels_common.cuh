@@ -1,13 +1,12 @@
-// kernels.cuh — sm_100a kernels of the WoP-PBS hot path (SURVEY.md §8a rows a3, a6, a9–a15, a17).
+// kernels_common.cuh — the integer / glue kernels of the WoP-PBS hot path (SURVEY.md §8a rows a3, a12 fallback, a17).
+// The FFT / external-product kernels live in kernels_ep.cuh, the tensor-core keyswitch GEMMs in kernels_gemm_umma.cuh.
 //
-//   lwe_gemm_kernel        K1/K5  batched LWE keyswitch and private functional packing keyswitch as an exact integer
-//                                 GEMM mod 2^64:  out[ct][col] = corr[col] − Σ_k digit'[ct][k]·key[k][col]
-//   pbs_kernel             K4     persistent blind rotation + sample extract (homomorphic_shift_boolean), B ciphertexts per
-//                                 CTA share every BSK load
-//   poly_fft_kernel        K2/K6  torus polynomial → Fourier slots (BSK conversion, GGSW fill_with_forward_fourier)
-//   vp_kernel              K7     vertical packing: blind rotation by the circuit-bootstrapped GGSWs + sample extract
-//   cmux_tree_kernel       K7     one CMux-tree layer (only when n_in > log2 N)
-//   aes_*_kernel           K8     AddRoundKey / ShiftRows+MixColumns / final round as gather-adds on the flat state
+//   pfks_digits_kernel     digits of the private functional packing keyswitch for the integer-pipe GEMM (base_log > 16)
+//   lwe_gemm_kernel        exact integer GEMM mod 2^64 on the integer pipe: out[ct][col] = corr[col] − Σ_k digit'[ct][k]·key[k][col]
+//                          (PFKS of params_sqrd_lvl_1, and the correction rows of both keyswitches at key upload)
+//   aes_*_kernel           AddRoundKey / ShiftRows+MixColumns+AddRoundKey / final round as gather-adds on the flat state
+//   lwe_add_kernel         leveled XOR (lwe_ciphertext_add_assign) over a batch
+//   negate_kernel, dfma_peak_kernel   key-upload helper, FP64 peak microbenchmark (roofline denominator)
 #pragma once
 #include <cuda_runtime.h>
 #include "tac_common.h"
@@ -17,16 +16,7 @@ namespace tac {
 
 // ================================================================================================ digits
 // bit-exact signed decomposition (tfhe SignedDecomposer), stored with the offset B/2 so that digits are non-negative:
-// digit' = digit + B/2 ∈ [0, B].  Key order of the keyswitch key: block i holds level l first ([U] lwe_keyswitch.rs).
-__global__ void ks_digits_kernel(const uint64_t* __restrict__ in, int nct, int big, int b, int l, uint32_t* __restrict__ dig) {
-    const size_t total = (size_t)nct * big;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
-        const size_t ct = idx / big; const int i = (int)(idx - ct * big);
-        uint64_t st = decomp_init_state(in[ct * (big + 1) + i], b, l);
-        uint32_t* o = dig + (ct * big + i) * l;
-        for (int s = 0; s < l; s++) o[s] = (uint32_t)(decomp_next(st, b) + (int64_t)(1u << (b - 1)));
-    }
-}
+// digit' = digit + B/2 ∈ [0, B].
 // PFKS: closest_representable first, all big+1 elements (mask and body), key block stores level 1 first and is iterated
 // reversed ([U] lwe_private_functional_packing_keyswitch.rs).
 __global__ void pfks_digits_kernel(const uint64_t* __restrict__ in, int nct, int big1, int b, int l, uint32_t* __restrict__ dig) {

@@ -198,15 +198,17 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+PBS_SOURCES = ("tac_common.h", "ep_core.cuh", "ep_step.cuh", "kernels_ep.cuh", "kernels_shape.inl", "kernels_n512.cu", "shape_launch.h")
+
+
 def csrc_digest():
-    """sha256 over the kernel sources (csrc/*.cu, *.cuh, *.inl, *.h): ties a committed ncu capture to the code it profiled
-    (the GPU box has no .git, so a commit hash cannot be checked there)"""
-    import glob
+    """sha256 over the sources `pbs_kernel` is compiled from: ties a committed ncu capture to the code it profiled (the GPU box
+    has no .git, so a commit hash cannot be checked there)"""
     import hashlib
     h = hashlib.sha256()
     d = os.path.join(ROOT, "tfhe-aes-2_b200", "csrc")
-    for f in sorted(glob.glob(os.path.join(d, "*.cu")) + glob.glob(os.path.join(d, "*.cuh")) + glob.glob(os.path.join(d, "*.inl")) + glob.glob(os.path.join(d, "*.h"))):
-        h.update(os.path.basename(f).encode() + b"\0" + open(f, "rb").read())
+    for name in PBS_SOURCES:
+        h.update(name.encode() + b"\0" + open(os.path.join(d, name), "rb").read())
     return h.hexdigest()[:16]
 
 

@@ -194,7 +194,7 @@ namespace aes_128 {
 using Block = std::array<uint8_t, 16>;
 using Key = std::array<uint8_t, 16>;
 constexpr int ROUNDS = 10;
-extern const uint8_t SBOX[256];
+extern const uint8_t* const SBOX;          // 256 entries, generated in aes_plain.cpp
 constexpr uint8_t RC[11] = {0x00, 0x01, 0x02, 0x04, 0x08, 0x10, 0x20, 0x40, 0x80, 0x1B, 0x36};
 inline uint8_t gf_256_mul(uint8_t a, uint8_t b) {                // src/aes_128.rs:42-56
     uint8_t res = 0;

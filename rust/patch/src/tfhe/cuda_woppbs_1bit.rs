@@ -203,10 +203,13 @@ impl FheContext {
         let glwe_noise = DynamicDistribution::new_gaussian_from_std_dev(StandardDev(p.glwe_noise_std));
         let pfks_noise = DynamicDistribution::new_gaussian_from_std_dev(StandardDev(p.pfks_noise_std));
 
+        // secret keys from an OS-seeded generator (the crate's engine copy, src/tfhe/engine.rs, only carries the encryption generator)
+        let mut seeder = new_seeder();
+        let mut secret_generator = SecretRandomGenerator::<DefaultRandomGenerator>::new(seeder.seed());
+        let glwe_sk: GlweSecretKeyOwned<u64> = allocate_and_generate_new_binary_glwe_secret_key(glwe_dim, poly, &mut secret_generator);
+        let lwe_sk: LweSecretKeyOwned<u64> = allocate_and_generate_new_binary_lwe_secret_key(lwe_dim, &mut secret_generator);
+
         let (glwe_secret_key, lwe_secret_key, bsk, ksk, pfpksk) = ShortintEngine::with_thread_local_mut(|engine| {
-            let glwe_sk: GlweSecretKeyOwned<u64> =
-                allocate_and_generate_new_binary_glwe_secret_key(glwe_dim, poly, &mut engine.secret_generator);
-            let lwe_sk: LweSecretKeyOwned<u64> = allocate_and_generate_new_binary_lwe_secret_key(lwe_dim, &mut engine.secret_generator);
             let bsk: LweBootstrapKeyOwned<u64> = par_allocate_and_generate_new_lwe_bootstrap_key(
                 &lwe_sk,
                 &glwe_sk,

@@ -154,6 +154,12 @@ int tac_aes_encrypt_blocks_dev(tac_ctx* ctx, int n_blocks, int rounds, int in_no
 /* ------------------------------------------------------------------ single stages (parity tests, profiling) */
 /* [U] keyswitch_lwe_ciphertext: [n_cts][kN+1] → [n_cts][n+1] */
 int tac_stage_keyswitch(tac_ctx* ctx, int n_cts, const uint64_t* in_host, uint64_t* out_host);
+/* [U] WopbsKey::extract_bits(DeltaLog(delta_log), ct, ExtractedBitsCount(n_bits)) — the general bit-extraction chain
+ * (keyswitch → bootstrap of the sign bit → subtract, least significant bit first): [n_cts][kN+1] → [n_cts][n_bits][n+1] under
+ * the small key, most significant extracted bit first, each carrying its bit at 2^63.  extract_dual_bit_from_bit
+ * (shortint_woppbs_1bit.rs:339-363) is the (63, 1) case = tac_stage_keyswitch; the 8-bit model uses (56, 8)
+ * (shortint_woppbs_8bit.rs:271-275). */
+int tac_extract_bits(tac_ctx* ctx, int delta_log, int n_bits, int n_cts, const uint64_t* in_host, uint64_t* out_host);
 /* [U] homomorphic_shift_boolean: [n_cts][n+1] → [n_cts][kN+1] */
 int tac_stage_pbs(tac_ctx* ctx, int n_cts, const uint64_t* in_host, uint64_t* out_host);
 /* [U] private_functional_keyswitch ×(k+1): [n_cts][kN+1] → [n_cts][k+1][(k+1)N] */

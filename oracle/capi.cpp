@@ -108,6 +108,12 @@ void orc_pbs_batch(void* h, const uint64_t* in_small, int n, uint64_t* out_big) 
 #pragma omp parallel for schedule(dynamic, 1)
     for (int i = 0; i < n; i++) pbs_shift_boolean(*ks, in_small + (size_t)i * S, out_big + (size_t)i * L);
 }
+void orc_extract_bits_batch(void* h, const uint64_t* in_big, int n, int delta_log, int n_bits, uint64_t* out_small) {
+    KeySet* ks = (KeySet*)h;
+    const size_t L = (size_t)ks->p.big() + 1, S = (size_t)ks->p.n + 1;
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int i = 0; i < n; i++) extract_bits(*ks, in_big + (size_t)i * L, delta_log, n_bits, out_small + (size_t)i * n_bits * S);
+}
 void orc_pfks_batch(void* h, const uint64_t* in_big, int n, uint64_t* out) {
     KeySet* ks = (KeySet*)h; const int L = ks->p.big() + 1; const size_t O = (size_t)(ks->p.k + 1) * (ks->p.k + 1) * ks->p.N;
 #pragma omp parallel for schedule(dynamic, 1)

@@ -413,8 +413,12 @@ void sample_extract0(int k, int N, const uint64_t* glwe, uint64_t* lwe) {
 // [U] fft64/crypto/wop_pbs.rs::homomorphic_shift_boolean (delta_log = 63 → pre-shift multiplier 1) wrapping
 //     fft64/crypto/bootstrap.rs::{blind_rotate_assign, bootstrap}
 void pbs_shift_boolean(const KeySet& ks, const uint64_t* in_small, uint64_t* out_big) {
+    pbs_sign(ks, in_small, 1ull << (63 - ks.p.cbs_b * ks.p.cbs_l), out_big);
+}
+// the bootstrap both callers share: accumulator = trivial GLWE with −alpha in every coefficient, input body + 2^62 (centres
+// the error on the negacyclic step), output body + alpha  ⇒  LWE of (sign bit of the input)·2·alpha under the big key
+void pbs_sign(const KeySet& ks, const uint64_t* in_small, uint64_t alpha, uint64_t* out_big) {
     const Params& p = ks.p; const int N = p.N, k = p.k, G = k + 1, M = N / 2, logN = ilog2(N);
-    const uint64_t alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
     std::vector<uint64_t> acc((size_t)G * N, 0ull), ct1((size_t)G * N), tmp(N);
     // accumulator = trivial GLWE, body = -alpha in every coefficient, rotated by X^{-b~}
     const uint64_t body_in = in_small[p.n] + (1ull << 62);
@@ -433,6 +437,27 @@ void pbs_shift_boolean(const KeySet& ks, const uint64_t* in_small, uint64_t* out
     }
     sample_extract0(k, N, acc.data(), out_big);
     out_big[(size_t)k * N] += alpha;
+}
+
+// [U] fft64/crypto/wop_pbs.rs::extract_bits — the general bit-extraction chain (the AES path calls it with delta_log = 63 and
+// one bit, where it degenerates to the keyswitch alone; reference shortint_woppbs_1bit.rs:342-349; the 8-bit model extracts 8
+// bits at delta_log 56, shortint_woppbs_8bit.rs:271-275).  For bit i = 0 … n_bits−1, least significant first:
+//   shifted = remaining · 2^(64 − delta_log − i − 1)            the bit becomes the most significant one
+//   out[n_bits − 1 − i] = keyswitch(shifted)                     small key; the list ends up most significant bit first
+//   (last bit: done)  bit_big = pbs_sign(keyswitch output, alpha = 2^(delta_log + i − 1))      = bit · 2^(delta_log + i)
+//   remaining −= bit_big                                         clears the bit for the next round
+void extract_bits(const KeySet& ks, const uint64_t* in_big, int delta_log, int n_bits, uint64_t* out_small /* [n_bits][n+1] */) {
+    const Params& p = ks.p; const int L = p.big() + 1, S = p.n + 1;
+    std::vector<uint64_t> rem(in_big, in_big + L), shifted(L), small(S), bit_big(L);
+    for (int i = 0; i < n_bits; i++) {
+        const int shift = 64 - delta_log - i - 1;
+        for (int t = 0; t < L; t++) shifted[t] = rem[t] << shift;
+        keyswitch(ks, shifted.data(), small.data());
+        memcpy(out_small + (size_t)(n_bits - 1 - i) * S, small.data(), sizeof(uint64_t) * S);
+        if (i == n_bits - 1) break;
+        pbs_sign(ks, small.data(), 1ull << (delta_log + i - 1), bit_big.data());
+        for (int t = 0; t < L; t++) rem[t] -= bit_big[t];
+    }
 }
 
 // [U] lwe_private_functional_packing_keyswitch.rs::private_functional_keyswitch_lwe_ciphertext_into_glwe_ciphertext, for all k+1 keys

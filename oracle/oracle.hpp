@@ -114,6 +114,8 @@ inline uint64_t decode_bit(uint64_t enc) { return ((enc + (1ull << 62)) & (1ull 
 // ---------------------------------------------------------------- server-side stages
 void keyswitch(const KeySet& ks, const uint64_t* in_big, uint64_t* out_small);
 void pbs_shift_boolean(const KeySet& ks, const uint64_t* in_small, uint64_t* out_big);
+void pbs_sign(const KeySet& ks, const uint64_t* in_small, uint64_t alpha, uint64_t* out_big);
+void extract_bits(const KeySet& ks, const uint64_t* in_big, int delta_log, int n_bits, uint64_t* out_small);
 void pfks_all(const KeySet& ks, const uint64_t* in_big, uint64_t* ggsw_level_out /* [k+1][(k+1)N] */);
 // Fourier GGSW (one per input bit): [s][r][c][M] re / im
 struct FourierGgsw { std::vector<double> re, im; };

@@ -102,6 +102,7 @@ extern "C" {
 
     // single stages, profiling
     pub fn tac_stage_keyswitch(ctx: *mut tac_ctx, n_cts: c_int, in_host: *const u64, out_host: *mut u64) -> c_int;
+    pub fn tac_extract_bits(ctx: *mut tac_ctx, delta_log: c_int, n_bits: c_int, n_cts: c_int, in_host: *const u64, out_host: *mut u64) -> c_int;
     pub fn tac_stage_pbs(ctx: *mut tac_ctx, n_cts: c_int, in_host: *const u64, out_host: *mut u64) -> c_int;
     pub fn tac_stage_pfks(ctx: *mut tac_ctx, n_cts: c_int, in_host: *const u64, out_host: *mut u64) -> c_int;
     pub fn tac_stage_vertical_packing(ctx: *mut tac_ctx, lut_id: c_int, batch: c_int, ggsw_std_host: *const u64, out_host: *mut u64) -> c_int;

@@ -66,6 +66,7 @@ def lib():
     L.orc_keyswitch_batch.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p]
     L.orc_pbs_batch.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p]
     L.orc_pfks_batch.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p]
+    L.orc_extract_bits_batch.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, C.c_int, _u64p]
     L.orc_external_product.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, _u64p, _u64p]
     L.orc_vertical_packing.argtypes = [C.c_void_p, _u64p, C.c_int, _u64p, C.c_int, _u64p]
     L.orc_circuit_bootstrap_batch.argtypes = [C.c_void_p, _u64p, C.c_int, C.c_int, _u64p, C.c_int, _u64p]
@@ -192,6 +193,13 @@ class Oracle:
         small = np.ascontiguousarray(small, dtype=np.uint64).reshape(-1, self.p.n + 1)
         out = np.empty((small.shape[0], self.big1), dtype=np.uint64)
         self.L.orc_pbs_batch(self.h, small, small.shape[0], out)
+        return out
+
+    def extract_bits(self, bigs, delta_log, n_bits):
+        """[U] wop_pbs.rs::extract_bits: [n][big+1] → [n][n_bits][small+1], most significant extracted bit first"""
+        bigs = np.ascontiguousarray(bigs, dtype=np.uint64).reshape(-1, self.big1)
+        out = np.empty((bigs.shape[0], n_bits, self.p.n + 1), dtype=np.uint64)
+        self.L.orc_extract_bits_batch(self.h, bigs, bigs.shape[0], delta_log, n_bits, out)
         return out
 
     def pfks(self, bigs):

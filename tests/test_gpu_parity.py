@@ -104,6 +104,33 @@ def test_poly_fft_matches_numpy(gpu64):
     assert np.abs(got - want).max() < 2.0**-40 * scale, np.log2(np.abs(got - want).max() / scale)
 
 
+def test_extract_bits_chain(gpu64, oracle64):
+    """[U] wop_pbs.rs::extract_bits beyond the one-bit case of the AES path: 3-bit messages at delta_log 61 — keyswitch,
+    bootstrap of the sign bit, subtract, three times.  The first (least significant) extraction is integer-only and must equal
+    the oracle's words.  The later ones follow an f64 bootstrap: two correct blind rotations agree on the phase but not on the
+    mask words, so the keyswitch that follows draws an independent noise realisation (σ ≈ 2^57) — they are compared on the
+    decoded bit and on the error band.  (63, 1) is the keyswitch itself."""
+    ck, ctx = gpu64
+    msgs = list(range(8)) + [5, 2]
+    cts = ck.encrypt_bits([0] * len(msgs), first_index=4242)
+    cts[:, -1] += np.array(msgs, dtype=np.uint64) << np.uint64(61)
+    got = ctx.extract_bits(cts, 61, 3)
+    ref = oracle64.extract_bits(cts, 61, 3)
+    assert np.array_equal(got[:, 2], ref[:, 2])                              # bit 0: shift + keyswitch only
+    ph_g = oracle64.phases_small(got.reshape(-1, got.shape[-1])).reshape(len(msgs), 3)
+    ph_r = oracle64.phases_small(ref.reshape(-1, ref.shape[-1])).reshape(len(msgs), 3)
+    bits = ((ph_g + np.uint64(1 << 62)) >> np.uint64(63)).astype(int)
+    assert [int("".join(map(str, b)), 2) for b in bits.tolist()] == msgs
+    want = bits.astype(np.uint64) << np.uint64(63)
+    e_g, e_r = signed(ph_g - want), signed(ph_r - want)
+    assert np.abs(e_g).max() < 2.0**61 and np.abs(e_r).max() < 2.0**61      # decoding margin 2^62
+    assert e_g.std() < 2 * e_r.std() + 2.0**55
+    one = ctx.extract_bits(cts[:3], 63, 1)
+    assert np.array_equal(one[:, 0], ctx.stage_keyswitch(cts[:3]))
+    with pytest.raises(RuntimeError, match="delta_log"):
+        ctx.extract_bits(cts[:1], 62, 3)
+
+
 def test_lwe_add_batch_bit_exact(gpu64):
     ck, ctx = gpu64
     rng = np.random.default_rng(3)

@@ -190,6 +190,19 @@ def test_oracle_increment_8bit_adder_9_to_9(oracle64, ol):
     assert oracle64.decrypt_bytes(value.reshape(-1, oracle64.big1)) == bytes([0x01, 0x01])
 
 
+def test_oracle_extract_bits_chain(oracle64):
+    # [U] wop_pbs.rs::extract_bits beyond the one-bit case: 3-bit messages at delta_log 61 come back bit for bit (most significant
+    # first), and (63, 1) — what extract_dual_bit_from_bit asks for (shortint_woppbs_1bit.rs:342-349) — is the keyswitch alone
+    msgs = [0, 3, 5, 6]
+    cts = oracle64.encrypt_bits([0] * len(msgs), first_index=900)
+    cts[:, -1] += np.array(msgs, dtype=np.uint64) << np.uint64(61)
+    out = oracle64.extract_bits(cts, 61, 3)
+    ph = oracle64.phases_small(out.reshape(-1, out.shape[-1])).reshape(len(msgs), 3)
+    bits = ((ph + np.uint64(1 << 62)) >> np.uint64(63)).astype(int)
+    assert [int("".join(map(str, b)), 2) for b in bits.tolist()] == msgs
+    assert np.array_equal(oracle64.extract_bits(cts[:2], 63, 1)[:, 0], oracle64.keyswitch(cts[:2]))
+
+
 def test_oracle_cmux_tree_16_to_8(ol):
     # reference :626-659 — 16 inputs at N = 1024 (params_sqrd_lvl_1) exercises the real CMux tree (6 tree bits)
     o = ol.Oracle(1, seed=77)

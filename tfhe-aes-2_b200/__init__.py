@@ -100,6 +100,7 @@ _SIGNATURES = {
     "tac_aes_encrypt_blocks": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tac_aes_encrypt_blocks_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "tac_stage_keyswitch": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
+    "tac_extract_bits": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, _u64p, _u64p]),
     "tac_stage_pbs": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "tac_stage_pfks": (C.c_int, [C.c_void_p, C.c_int, _u64p, _u64p]),
     "tac_stage_vertical_packing": (C.c_int, [C.c_void_p, C.c_int, C.c_int, _u64p, _u64p]),
@@ -594,6 +595,13 @@ class FheContext(NoiseContext):
         a = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.params.big_lwe_size)
         out = np.empty((a.shape[0], self.params.lwe_dimension + 1), dtype=np.uint64)
         self._check(self.L.tac_stage_keyswitch(self.h, a.shape[0], a, out))
+        return out
+
+    def extract_bits(self, cts, delta_log, n_bits):
+        """WopbsKey::extract_bits: [n][big+1] → [n][n_bits][small+1], most significant extracted bit first"""
+        a = np.ascontiguousarray(cts, dtype=np.uint64).reshape(-1, self.params.big_lwe_size)
+        out = np.empty((a.shape[0], n_bits, self.params.lwe_dimension + 1), dtype=np.uint64)
+        self._check(self.L.tac_extract_bits(self.h, delta_log, n_bits, a.shape[0], a, out.reshape(-1)))
         return out
 
     def stage_pbs(self, small):

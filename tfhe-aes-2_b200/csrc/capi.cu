@@ -189,10 +189,11 @@ int gemm(tac_ctx* ctx, const uint32_t* dig, int nct, int Kd, const uint64_t* key
     return post_launch(ctx, "lwe_gemm_kernel");
 }
 
-int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out) {
+// alpha: the bootstrap returns (sign bit of the input)·2·alpha; circuit bootstrapping uses 2^(63 − cbs_b·level), bit extraction 2^(delta_log + i − 1)
+int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out, uint64_t alpha = 0) {
     if (nct == 0) return TAC_OK;
     const TacParams& p = ctx->p;
-    const uint64_t alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
+    if (alpha == 0) alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
     return check_launch(ctx, ctx->ops->pbs(klaunch(ctx), p.pbs_l, small, nct, p.n, ctx->bsk_f, p.pbs_b, alpha, out), "pbs_kernel");
 }
 
@@ -851,6 +852,40 @@ int tac_stage_pbs(tac_ctx* ctx, int n, const uint64_t* in_host, uint64_t* out_ho
     CU(cudaMemcpyAsync(ctx->ws_small.p, in_host, ib, cudaMemcpyHostToDevice, ctx->stream));
     TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), n, ctx->ws_pbs.as<uint64_t>()));
     CU(cudaMemcpyAsync(out_host, ctx->ws_pbs.p, ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return TAC_OK;
+}
+// [U] fft64/crypto/wop_pbs.rs::extract_bits — WopbsKey::extract_bits(DeltaLog, ct, ExtractedBitsCount): the general chain
+// keyswitch → bootstrap of the sign → subtract, least significant bit first; output list most significant bit first.
+// The AES path calls it with (63, 1), which is the keyswitch alone (reference shortint_woppbs_1bit.rs:342-349).
+int tac_extract_bits(tac_ctx* ctx, int delta_log, int n_bits, int n_cts, const uint64_t* in_host, uint64_t* out_host) {
+    LOCK(ctx);
+    CU(cudaSetDevice(ctx->device));
+    if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
+    if (n_bits < 1 || delta_log < 1 || delta_log + n_bits > 64) return fail(ctx, TAC_ERR_ARG, "need 1 <= delta_log and delta_log + n_bits <= 64");
+    if (n_cts <= 0) return n_cts == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative count");
+    const size_t L = (size_t)ctx->big() + 1, S = (size_t)ctx->p.n + 1, total = (size_t)n_cts * L;
+    TRY(ensure(ctx, ctx->ws_in, total * 8));                 // remaining
+    TRY(ensure(ctx, ctx->ws_state, total * 8));              // shifted
+    TRY(ensure(ctx, ctx->ws_pbs, total * 8));                // bootstrapped bit
+    TRY(ensure(ctx, ctx->ws_small, (size_t)n_cts * S * 8));
+    TRY(ensure(ctx, ctx->ws_out, (size_t)n_cts * n_bits * S * 8));
+    uint64_t* rem = ctx->ws_in.as<uint64_t>();
+    uint64_t* shifted = ctx->ws_state.as<uint64_t>();
+    CU(cudaMemcpyAsync(rem, in_host, total * 8, cudaMemcpyHostToDevice, ctx->stream));
+    const int g = grid1d(total, 256, ctx->sm_count);
+    for (int i = 0; i < n_bits; i++) {
+        lwe_shl_kernel<<<g, 256, 0, ctx->stream>>>(rem, 64 - delta_log - i - 1, total, shifted);
+        TRY(post_launch(ctx, "lwe_shl_kernel"));
+        TRY(stage_ks(ctx, shifted, n_cts, ctx->ws_small.as<uint64_t>()));
+        CU(cudaMemcpy2DAsync(ctx->ws_out.as<uint64_t>() + (size_t)(n_bits - 1 - i) * S, (size_t)n_bits * S * 8, ctx->ws_small.p, S * 8, S * 8, (size_t)n_cts,
+                             cudaMemcpyDeviceToDevice, ctx->stream));
+        if (i == n_bits - 1) break;
+        TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), n_cts, ctx->ws_pbs.as<uint64_t>(), 1ull << (delta_log + i - 1)));
+        lwe_sub_kernel<<<g, 256, 0, ctx->stream>>>(rem, ctx->ws_pbs.as<uint64_t>(), total);
+        TRY(post_launch(ctx, "lwe_sub_kernel"));
+    }
+    CU(cudaMemcpyAsync(out_host, ctx->ws_out.p, (size_t)n_cts * n_bits * S * 8, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     return TAC_OK;
 }

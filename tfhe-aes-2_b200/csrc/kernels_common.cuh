@@ -5,7 +5,7 @@
 //   lwe_gemm_kernel        exact integer GEMM mod 2^64 on the integer pipe: out[ct][col] = corr[col] − Σ_k digit'[ct][k]·key[k][col]
 //                          (PFKS of params_sqrd_lvl_1, and the correction rows of both keyswitches at key upload)
 //   aes_*_kernel           AddRoundKey / ShiftRows+MixColumns+AddRoundKey / final round as gather-adds on the flat state
-//   lwe_add_kernel         leveled XOR (lwe_ciphertext_add_assign) over a batch
+//   lwe_add_kernel         leveled XOR (lwe_ciphertext_add_assign) over a batch; lwe_shl_kernel / lwe_sub_kernel: glue of extract_bits
 //   negate_kernel, dfma_peak_kernel   key-upload helper, FP64 peak microbenchmark (roofline denominator)
 #pragma once
 #include <cuda_runtime.h>
@@ -126,6 +126,13 @@ __global__ void aes_final_round_kernel(const uint64_t* __restrict__ sub, const u
 // leveled XOR (BitXorAssign, shortint_woppbs_1bit.rs:134-142 → lwe_ciphertext_add_assign): a += b, element-wise
 __global__ void lwe_add_kernel(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, size_t total) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) a[i] += b[i];
+}
+// bit extraction glue ([U] wop_pbs.rs::extract_bits): out = a · 2^shift, a −= b
+__global__ void lwe_shl_kernel(const uint64_t* __restrict__ a, int shift, size_t total, uint64_t* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) out[i] = a[i] << shift;
+}
+__global__ void lwe_sub_kernel(uint64_t* __restrict__ a, const uint64_t* __restrict__ b, size_t total) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) a[i] -= b[i];
 }
 __global__ void negate_kernel(uint64_t* __restrict__ a, size_t total) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) a[i] = 0ull - a[i];

@@ -486,14 +486,15 @@ void pfks_all(const KeySet& ks, const uint64_t* in_big, uint64_t* out) {
     }
 }
 
-// [U] wop_pbs.rs::circuit_bootstrap_boolean (cbs level index 0 ↔ decomposition level 1; all shipped sets have cbs_l = 1)
+// [U] wop_pbs.rs::circuit_bootstrap_boolean (cbs level index 0 ↔ decomposition level 1; the four shipped sets have cbs_l = 1)
 void circuit_bootstrap_boolean(const KeySet& ks, const uint64_t* in_small, uint64_t* ggsw_std) {
     const Params& p = ks.p; const int G = p.k + 1, W = G * p.N;
-    if (p.cbs_l != 1) { fprintf(stderr, "oracle: cbs_level != 1 not supported\n"); abort(); }
     std::vector<uint64_t> lwe(p.big() + 1);
-    pbs_shift_boolean(ks, in_small, lwe.data());
-    pfks_all(ks, lwe.data(), ggsw_std);
-    (void)W;
+    // one bootstrap + (k+1) private functional keyswitches per level: level matrix s of the GGSW carries bit · q / B^(s+1)
+    for (int lv = 1; lv <= p.cbs_l; lv++) {
+        pbs_sign(ks, in_small, 1ull << (63 - p.cbs_b * lv), lwe.data());
+        pfks_all(ks, lwe.data(), ggsw_std + (size_t)(lv - 1) * G * W);
+    }
 }
 // [U] ggsw.rs::FourierGgswCiphertext::fill_with_forward_fourier
 void ggsw_to_fourier(const KeySet& ks, const uint64_t* ggsw_std, int levels, FourierGgsw& out) {

@@ -364,6 +364,33 @@ def test_keys_and_ciphertexts_through_wire_files(tac, ck64, ol, tmp_path):
         other.load_keys(kf)
 
 
+def test_two_level_circuit_bootstrap(tac, ck64, oracle64, ol):
+    """cbs_level = 2 (base 2^8): one bootstrap + (k+1) PFKS per level, 2-level GGSWs in the vertical packing — decrypt-checked,
+    against the oracle with the same parameters on the same keys (evaluation keys do not depend on the cbs decomposition), and
+    with output noise no worse than the one-level set's"""
+    p = tac.params_preset(64)
+    p.cbs_level, p.cbs_base_log = 2, 8
+    ctx = tac.FheContext(p)
+    ctx.upload_keys(ck64)
+    po = ol.preset(64)
+    po.cbs_l, po.cbs_b = 2, 8
+    orc = ol.Oracle(po, seed=0, raw=(ck64.sk_glwe, ck64.sk_lwe, ck64.bsk, ck64.ksk, ck64.pfpksk))
+    lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    vals = [0x00, 0x53, 0xCA, 0xFF, 0x3C]
+    cts = ck64.encrypt_bytes(bytes(vals))
+    out = ctx.circuit_bootstrap_batch(cts, lut)
+    assert ck64.decrypt_bytes(out.reshape(-1, p.big_lwe_size)) == bytes(ol.sbox(v) for v in vals)
+    ref = orc.circuit_bootstrap(cts[:1], lut.table, 8)
+    assert ck64.decrypt_bytes(ref.reshape(-1, p.big_lwe_size)) == bytes([ol.sbox(vals[0])])
+    want = ck64.decrypt_bits(out.reshape(-1, p.big_lwe_size)).astype(np.uint64) << np.uint64(63)
+    err = signed(ck64.decrypt_phases(out) - want)
+    assert np.abs(err).max() < 2.0**60 and err.std() < 2.0**57
+    bad = tac.params_preset(64)
+    bad.cbs_level = 3
+    with pytest.raises(RuntimeError, match="cbs_level"):
+        tac.FheContext(bad)
+
+
 def test_wopbs_empty_batch(gpu64, ol):
     ck, ctx = gpu64
     lut = ctx.generate_lookup_table(8, 8, lambda b: ol.sbox(b))

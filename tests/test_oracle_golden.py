@@ -203,6 +203,18 @@ def test_oracle_extract_bits_chain(oracle64):
     assert np.array_equal(oracle64.extract_bits(cts[:2], 63, 1)[:, 0], oracle64.keyswitch(cts[:2]))
 
 
+def test_oracle_two_level_circuit_bootstrap(oracle64, ol):
+    # [U] wop_pbs.rs::circuit_bootstrap_boolean with cbs_level = 2 (the reference's 8-bit model uses 4 levels,
+    # shortint_woppbs_8bit.rs; the 1-bit sets use 1): one bootstrap + (k+1) PFKS per level, vertical packing with 2-level GGSWs.
+    # Evaluation keys do not depend on the circuit-bootstrap decomposition, so the lvl_64 keys are reused.
+    p = ol.preset(64)
+    p.cbs_l, p.cbs_b = 2, 8
+    o = ol.Oracle(p, seed=0, raw=(oracle64.sk_glwe, oracle64.sk_lwe, oracle64.bsk, oracle64.ksk, oracle64.pfpksk))
+    lut = o.generate_lookup_table(8, 8, lambda b: ol.sbox(b))
+    out = o.circuit_bootstrap(oracle64.encrypt_bytes([0x53])[0], lut, 8)
+    assert oracle64.decrypt_bytes(out) == bytes([ol.sbox(0x53)])
+
+
 def test_oracle_cmux_tree_16_to_8(ol):
     # reference :626-659 — 16 inputs at N = 1024 (params_sqrd_lvl_1) exercises the real CMux tree (6 tree bits)
     o = ol.Oracle(1, seed=77)

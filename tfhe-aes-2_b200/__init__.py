@@ -619,7 +619,7 @@ class FheContext(NoiseContext):
 
     def stage_vertical_packing(self, ggsw_std, lut):
         G, N = self.params.glwe_dimension + 1, self.params.polynomial_size
-        g = np.ascontiguousarray(ggsw_std, dtype=np.uint64).reshape(-1, lut.input_bits, G, G * N)
+        g = np.ascontiguousarray(ggsw_std, dtype=np.uint64).reshape(-1, lut.input_bits, self.params.cbs_level, G, G * N)
         out = np.empty((g.shape[0], lut.output_bits, self.params.big_lwe_size), dtype=np.uint64)
         self._check(self.L.tac_stage_vertical_packing(self.h, lut.device_id(self), g.shape[0], g.reshape(-1), out.reshape(-1)))
         return out

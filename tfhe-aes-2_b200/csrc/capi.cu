@@ -152,8 +152,8 @@ std::string unsupported_params(const TacParams& p) {
     if ((p.n & 1) == 0) return "lwe_dimension must be odd (the integer GEMM works on column pairs of the (n+1)-wide keyswitch key)";
     if (p.pbs_l < 1 || p.pbs_l > 4 || p.pbs_b < 1 || p.pbs_b > 15 || p.pbs_b * p.pbs_l > 63)
         return "pbs decomposition: need level <= 4, base_log <= 15 (digits are cached as 16-bit fields)";
-    if (p.cbs_l != 1) return "cbs_level != 1 (multi-level circuit bootstrapping) is not supported";
-    if (p.cbs_b < 1 || p.cbs_b > 15) return "cbs_base_log must be in [1, 15]";
+    if (p.cbs_l < 1 || p.cbs_l > 2) return "cbs_level must be 1 or 2 (the vertical-packing kernels are instantiated for these)";
+    if (p.cbs_b < 1 || p.cbs_b > 15 || p.cbs_b * p.cbs_l > 62) return "cbs_base_log must be in [1, 15]";
     if (p.ks_l < 1 || p.ks_b < 1 || p.ks_b > 7 || p.ks_b * p.ks_l > 63) return "keyswitch decomposition: base_log must be <= 7 (one byte limb on the tensor cores)";
     if (p.pfks_l < 1 || p.pfks_b < 1 || p.pfks_b > 31 || p.pfks_b * p.pfks_l > 63) return "pfks decomposition: base_log must be <= 31";
     // s32 tensor-memory accumulators hold 2 byte-limb products per k: exact while K·2·255² < 2^31
@@ -197,7 +197,7 @@ int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out, uint64_t al
     return check_launch(ctx, ctx->ops->pbs(klaunch(ctx), p.pbs_l, small, nct, p.n, ctx->bsk_f, p.pbs_b, alpha, out), "pbs_kernel");
 }
 
-// vertical packing of `nbox` boxes from Fourier GGSWs ([nbox][n_in][1][G][G][M]) → out [nbox][n_out][big+1]
+// vertical packing of `nbox` boxes from Fourier GGSWs ([nbox][n_in][cbs_l][G][G][M]) → out [nbox][n_out][big+1]
 int vertical_packing(tac_ctx* ctx, const Lut& lut, const cplx* ggsw_f, int nbox, uint64_t* out) {
     const TacParams& p = ctx->p;
     const int logN = ilog2(p.N);
@@ -214,13 +214,13 @@ int vertical_packing(tac_ctx* ctx, const Lut& lut, const cplx* ggsw_f, int nbox,
         int which = 0;
         for (int j = 0; j < tree_bits; j++) {
             uint64_t* dst = bufs[which];
-            TRY(check_launch(ctx, ctx->ops->tree(klaunch(ctx), ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst),
+            TRY(check_launch(ctx, ctx->ops->tree(klaunch(ctx), p.cbs_l, ggsw_f, nbox, lut.n_in, tree_bits - 1 - j, lut.dev, lut.len, cur, nodes, lut.n_out, p.cbs_b, dst),
                              "cmux_tree_kernel"));
             cur = dst; which ^= 1; nodes /= 2;
         }
         init = cur;
     }
-    return check_launch(ctx, ctx->ops->vp(klaunch(ctx), ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out), "vp_kernel");
+    return check_launch(ctx, ctx->ops->vp(klaunch(ctx), p.cbs_l, ggsw_f, nbox, lut.n_in, tree_bits, lut.dev, lut.len, init, lut.n_out, p.cbs_b, out), "vp_kernel");
 }
 
 int stage_event(tac_ctx* ctx, int idx) {
@@ -289,26 +289,36 @@ int stage_pfks(tac_ctx* ctx, const uint64_t* in, int nct, uint64_t* ggsw) {
 int wopbs_dev(tac_ctx* ctx, const Lut& lut, int nbox, const uint64_t* in, uint64_t* out) {
     const TacParams& p = ctx->p;
     if (!ctx->keys_valid) return fail(ctx, TAC_ERR_STATE, "evaluation keys not uploaded");
-    const int big1 = ctx->big() + 1, G = ctx->G(), M = p.N / 2;
+    const int big1 = ctx->big() + 1, G = ctx->G(), M = p.N / 2, lc = p.cbs_l;
     const size_t ggsw_words = (size_t)G * G * p.N;
-    const int max_boxes = (int)std::max<size_t>(1, ctx->max_cts / lut.n_in);
+    const int max_boxes = (int)std::max<size_t>(1, ctx->max_cts / ((size_t)lut.n_in * lc));
     for (int b0 = 0; b0 < nbox; b0 += max_boxes) {
         const int nb = std::min(max_boxes, nbox - b0);
         const int nct = nb * lut.n_in;
         const uint64_t* cin = in + (size_t)b0 * lut.n_in * big1;
         uint64_t* cout = out + (size_t)b0 * lut.n_out * big1;
         TRY(ensure(ctx, ctx->ws_small, (size_t)nct * (p.n + 1) * 8));
-        TRY(ensure(ctx, ctx->ws_pbs, (size_t)nct * big1 * 8));
-        TRY(ensure(ctx, ctx->ws_ggsw, (size_t)nct * ggsw_words * 8));
-        TRY(ensure(ctx, ctx->ws_ggswf, (size_t)nct * G * G * M * sizeof(cplx)));
+        TRY(ensure(ctx, ctx->ws_pbs, (size_t)nct * lc * big1 * 8));
+        TRY(ensure(ctx, ctx->ws_ggsw, (size_t)nct * lc * ggsw_words * 8));
+        TRY(ensure(ctx, ctx->ws_ggswf, (size_t)nct * lc * G * G * M * sizeof(cplx)));
         TRY(stage_event(ctx, 0));
         TRY(stage_ks(ctx, cin, nct, ctx->ws_small.as<uint64_t>()));                       // extract_dual_bit_from_bit
         TRY(stage_event(ctx, 1));
-        TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), nct, ctx->ws_pbs.as<uint64_t>()));      // homomorphic_shift_boolean
+        // circuit_bootstrap_boolean: one homomorphic_shift_boolean per level (all four shipped parameter sets have one level)
+        if (lc == 1) {
+            TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), nct, ctx->ws_pbs.as<uint64_t>()));
+        } else {
+            TRY(ensure(ctx, ctx->ws_tree_a, (size_t)nct * big1 * 8));
+            for (int lv = 1; lv <= lc; lv++) {          // level lv lands at [ct][lv-1] so that the PFKS rows come out as [ct][level][row]
+                TRY(pbs(ctx, ctx->ws_small.as<uint64_t>(), nct, ctx->ws_tree_a.as<uint64_t>(), 1ull << (63 - p.cbs_b * lv)));
+                CU(cudaMemcpy2DAsync(ctx->ws_pbs.as<uint64_t>() + (size_t)(lv - 1) * big1, (size_t)lc * big1 * 8, ctx->ws_tree_a.p, (size_t)big1 * 8,
+                                     (size_t)big1 * 8, (size_t)nct, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
         TRY(stage_event(ctx, 2));
-        TRY(stage_pfks(ctx, ctx->ws_pbs.as<uint64_t>(), nct, ctx->ws_ggsw.as<uint64_t>()));
+        TRY(stage_pfks(ctx, ctx->ws_pbs.as<uint64_t>(), nct * lc, ctx->ws_ggsw.as<uint64_t>()));
         TRY(stage_event(ctx, 3));
-        TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), (size_t)nct * G * G, ctx->ws_ggswf.as<cplx>()));   // fill_with_forward_fourier
+        TRY(poly_fft(ctx, ctx->ws_ggsw.as<uint64_t>(), (size_t)nct * lc * G * G, ctx->ws_ggswf.as<cplx>()));   // fill_with_forward_fourier
         TRY(stage_event(ctx, 4));
         TRY(vertical_packing(ctx, lut, ctx->ws_ggswf.as<cplx>(), nb, cout));
         TRY(stage_event(ctx, 5));
@@ -908,7 +918,7 @@ int tac_stage_vertical_packing(tac_ctx* ctx, int lut_id, int batch, const uint64
     const Lut* lut; TRY(get_lut(ctx, lut_id, &lut));
     if (batch <= 0) return batch == 0 ? TAC_OK : fail(ctx, TAC_ERR_ARG, "negative batch");
     const int G = ctx->G(), M = ctx->p.N / 2;
-    const size_t nct = (size_t)batch * lut->n_in;
+    const size_t nct = (size_t)batch * lut->n_in * ctx->p.cbs_l;              // GGSW level matrices
     const size_t ib = nct * G * G * ctx->p.N * 8, ob = (size_t)batch * lut->n_out * (ctx->big() + 1) * 8;
     TRY(ensure(ctx, ctx->ws_ggsw, ib)); TRY(ensure(ctx, ctx->ws_ggswf, nct * G * G * M * sizeof(cplx))); TRY(ensure(ctx, ctx->ws_out, ob));
     CU(cudaMemcpyAsync(ctx->ws_ggsw.p, ggsw_std_host, ib, cudaMemcpyHostToDevice, ctx->stream));

@@ -63,35 +63,54 @@ cudaError_t s_pbs(const KLaunch& k, int levels, const uint64_t* small, int nct, 
     return cudaErrorInvalidValue;
 }
 
-template <int B, int NT>
+#ifndef TAC_CBS_LEVELS
+#define TAC_CBS_LEVELS(X) X(1) X(2)          // circuit-bootstrap level counts the vertical-packing kernels are instantiated for
+#endif
+template <int L, int B, int NT>
 cudaError_t launch_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
                       const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
-    typedef EpCfg<SN, SK, 1, B> C;
+    typedef EpCfg<SN, SK, L, B> C;
     const size_t smem = EpSmem<C>::bytes;
-    TAC_SET_SMEM((vp_kernel<SN, SK, 1, B, NT>), smem);
+    TAC_SET_SMEM((vp_kernel<SN, SK, L, B, NT>), smem);
     dim3 grid((n_out + B - 1) / B, nbox);
-    vp_kernel<SN, SK, 1, B, NT><<<grid, NT, smem, k.stream>>>(ggsw_f, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, k.wT, out);
+    vp_kernel<SN, SK, L, B, NT><<<grid, NT, smem, k.stream>>>(ggsw_f, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, k.wT, out);
     return cudaGetLastError();
 }
-cudaError_t s_vp(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
-                 const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
+template <int L>
+cudaError_t vp_levels(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+                      const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
 #if TAC_N == 512
     // 3 outputs per CTA with 256 threads (222 registers, no spills) measured 20 % faster on B200 than 4 outputs with 320
     // threads (168-register cap, spills) and 28 % faster than 2 outputs with 160 threads
-    if (n_out >= 3) return launch_vp<3, 256>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
-    if (n_out == 2) return launch_vp<2, 160>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    if (n_out >= 3) return launch_vp<L, 3, 256>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    if (n_out == 2) return launch_vp<L, 2, 160>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
 #endif
-    return launch_vp<1, 128>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    return launch_vp<L, 1, 128>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+}
+cudaError_t s_vp(const KLaunch& k, int levels, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+                 const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out) {
+#define X(LV) if (levels == LV) return vp_levels<LV>(k, ggsw_f, nbox, n_in, first, lut, lut_stride, init_glwe, n_out, base_log, out);
+    TAC_CBS_LEVELS(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
-cudaError_t s_tree(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
-                   const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
-    typedef EpCfg<SN, SK, 1, 1> C;
+template <int L>
+cudaError_t tree_levels(const KLaunch& k, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
+                        const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
+    typedef EpCfg<SN, SK, L, 1> C;
     const size_t smem = EpSmem<C>::bytes + (size_t)C::G * SN * sizeof(uint64_t);
-    TAC_SET_SMEM((cmux_tree_kernel<SN, SK, 1, 128>), smem);
+    TAC_SET_SMEM((cmux_tree_kernel<SN, SK, L, 128>), smem);
     dim3 grid(n_nodes_in / 2, n_out, nbox);
-    cmux_tree_kernel<SN, SK, 1, 128><<<grid, 128, smem, k.stream>>>(ggsw_f, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log, k.wT, node_out);
+    cmux_tree_kernel<SN, SK, L, 128><<<grid, 128, smem, k.stream>>>(ggsw_f, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log, k.wT, node_out);
     return cudaGetLastError();
+}
+cudaError_t s_tree(const KLaunch& k, int levels, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
+                   const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out) {
+#define X(LV) if (levels == LV) return tree_levels<LV>(k, ggsw_f, nbox, n_in, ggsw_idx, lut, lut_stride, node_in, n_nodes_in, n_out, base_log, node_out);
+    TAC_CBS_LEVELS(X)
+#undef X
+    return cudaErrorInvalidValue;
 }
 
 // one CMux-with-rotation step per accumulator (B = 1 CTA each) — test entry point for the FFT / external-product core

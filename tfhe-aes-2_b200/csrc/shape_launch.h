@@ -20,11 +20,12 @@ struct ShapeOps {
     // homomorphic_shift_boolean with `levels` BSK levels; cudaErrorInvalidValue if that level count is not instantiated
     cudaError_t (*pbs)(const KLaunch&, int levels, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha,
                        uint64_t* out);
-    // blind-rotation part of vertical packing (GGSWs n_in-1 … first), 1 level
-    cudaError_t (*vp)(const KLaunch&, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
+    // blind-rotation part of vertical packing (GGSWs n_in-1 … first) with `levels` circuit-bootstrap levels;
+    // cudaErrorInvalidValue if that level count is not instantiated
+    cudaError_t (*vp)(const KLaunch&, int levels, const double2* ggsw_f, int nbox, int n_in, int first, const uint64_t* lut, size_t lut_stride,
                       const uint64_t* init_glwe, int n_out, int base_log, uint64_t* out);
-    // one CMux-tree layer, 1 level
-    cudaError_t (*tree)(const KLaunch&, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
+    // one CMux-tree layer
+    cudaError_t (*tree)(const KLaunch&, int levels, const double2* ggsw_f, int nbox, int n_in, int ggsw_idx, const uint64_t* lut, size_t lut_stride,
                         const uint64_t* node_in, int n_nodes_in, int n_out, int base_log, uint64_t* node_out);
     // one CMux-with-rotation step per accumulator (test entry point)
     cudaError_t (*cmux_test)(const KLaunch&, int levels, const double2* ggsw_f, const int* rot, int base_log, int n_acc, uint64_t* acc);

@@ -157,7 +157,7 @@ def test_context_rejects_unsupported_parameter_sets(tac):
     assert "base_log must be <= 7" in err_for(ks_base_log=8)
     assert "must be odd" in err_for(lwe_dimension=676)
     assert "16-bit fields" in err_for(pbs_base_log=16)
-    assert "cbs_level" in err_for(cbs_level=2)
+    assert "cbs_level" in err_for(cbs_level=3)
     assert "below 16000" in err_for(ks_level=8, ks_base_log=2)
     assert "unsupported (polynomial_size" in err_for(polynomial_size=2048)
 

@@ -427,7 +427,7 @@ def run_gpu(args):
             "e2e": {"value": e2e_value, "unit": "blocks/s", "h2d_bytes_per_step": int(in_host.numel() * 8 * world),
                     "d2h_bytes_per_step": int(out_host.numel() * 8 * world), "steps": e2e_steps},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "kernel": "pbs_kernel<N=512,k=4,l=3,B=3,256 threads>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "fp64", "kernel": "pbs_merged_kernel<N=512,k=4,l=3,B=3,256 threads>", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": pbs_traffic(int(n_ct_per_launch)),
                          "peak_source": "DFMA microbenchmark in this run (FP64 is not in MEASURED_PEAKS.json)",
                          "peak_nominal": 37.2, "frac_of_nominal": achieved / 37.2, "peak_nominal_source": "148 SM x 64 DFMA/clk x 2 flop x 1.965 GHz",

@@ -9,6 +9,8 @@ Bars:
     the oracle itself shows;
   * everything end to end — decrypts to clear AES / the clear function.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -194,8 +196,18 @@ def test_pbs_batch_size_independent(gpu64, oracle64):
     small = oracle64.keyswitch(ck.encrypt_bits(rng.integers(0, 2, 12)))
     big_batch = np.concatenate([small, rng.integers(0, 2**64, (600 - 12, small.shape[1]), dtype=np.uint64)])
     alone = ctx.stage_pbs(small)                 # 12 ciphertexts: pbs_wide_kernel
-    together = ctx.stage_pbs(big_batch)[:12]     # 600 ciphertexts: pbs_kernel, B = 3 (wave-count cost model)
+    together = ctx.stage_pbs(big_batch)[:12]     # 600 ciphertexts: pbs_merged_kernel, B = 3 (wave-count cost model)
     assert np.array_equal(alone, together)
+    # the throughput kernel is instantiated with the shipped base log folded in at compile time and with a run-time one
+    os.environ["TAC_PBS_GENERIC_BASE_LOG"] = "1"
+    try:
+        generic = ctx.stage_pbs(big_batch)[:12]
+    finally:
+        del os.environ["TAC_PBS_GENERIC_BASE_LOG"]
+    assert np.array_equal(generic, together)
+    # ragged tail: a batch that does not fill its last CTA
+    ragged = ctx.stage_pbs(big_batch[:598])
+    assert np.array_equal(ragged[:12], together) and np.array_equal(ragged[12:], ctx.stage_pbs(big_batch)[12:598])
 
 
 def test_vertical_packing_from_oracle_ggsws(gpu64, oracle64, ol):

@@ -194,7 +194,7 @@ int pbs(tac_ctx* ctx, const uint64_t* small, int nct, uint64_t* out, uint64_t al
     if (nct == 0) return TAC_OK;
     const TacParams& p = ctx->p;
     if (alpha == 0) alpha = 1ull << (63 - p.cbs_b * p.cbs_l);
-    return check_launch(ctx, ctx->ops->pbs(klaunch(ctx), p.pbs_l, small, nct, p.n, ctx->bsk_f, p.pbs_b, alpha, out), "pbs_kernel");
+    return check_launch(ctx, ctx->ops->pbs(klaunch(ctx), p.pbs_l, small, nct, p.n, ctx->bsk_f, p.pbs_b, alpha, out), "pbs kernel");
 }
 
 // vertical packing of `nbox` boxes from Fourier GGSWs ([nbox][n_in][cbs_l][G][G][M]) → out [nbox][n_out][big+1]

@@ -242,6 +242,21 @@ TAC_HD void fft_fwd_pass1(int t, Src src, cplx* __restrict__ S) {
     dft_fwd_twisted<N>(v);
     static_for<0, P>([&](auto qc) { constexpr int q = decltype(qc)::value; S[slot_of(q, t)] = v[q]; });
 }
+// `src(mc, a, b)` receives the register row m as a compile-time constant (std::integral_constant), sample jj = t + 16m:
+// for sources that live in per-thread register arrays (pbs_merged_kernel keeps the digits of all levels in registers)
+template <int N, class Src>
+TAC_HD void fft_fwd_pass1_m(int t, Src src, cplx* __restrict__ S) {
+    constexpr int M = N / 2, P = M / 16;
+    cplx v[P];
+    static_for<0, P>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        double a, b;
+        src(mc, a, b);
+        v[bitrev<P>(m)] = mk(a, b);
+    });
+    dft_fwd_twisted<N>(v);
+    static_for<0, P>([&](auto qc) { constexpr int q = decltype(qc)::value; S[slot_of(q, t)] = v[q]; });
+}
 // ------------------------------------------------------------------------------------------------ forward, pass 2 (in place)
 // The 15 butterfly twiddles of lane q do not depend on the data: a caller can fetch them into registers BEFORE pass 1
 // (fft_fwd_twiddles), so that those shared-memory reads overlap the FP64 work of pass 1 instead of lengthening the load
@@ -358,6 +373,20 @@ TAC_HD void fft_inv_passB(int t, const cplx* __restrict__ S, Sink sink) {
         constexpr int m = decltype(mc)::value;
         const cplx z = mul_w128<false, m * CSTEP>(v[m]);
         sink(t + 16 * m, z.x, z.y);
+    });
+}
+
+// `sink(mc, re, im)` with the register row m as a compile-time constant (samples t + 16m and t + 16m + M)
+template <int N, class Sink>
+TAC_HD void fft_inv_passB_m(int t, const cplx* __restrict__ S, Sink sink) {
+    constexpr int M = N / 2, P = M / 16, CSTEP = 1024 / N;
+    cplx v[P];
+    static_for<0, P>([&](auto ic) { constexpr int i = decltype(ic)::value; v[i] = S[slot_of(bitrev<P>(i), t)]; });
+    dft_inv<P>(v);
+    static_for<0, P>([&](auto mc) {
+        constexpr int m = decltype(mc)::value;
+        const cplx z = mul_w128<false, m * CSTEP>(v[m]);
+        sink(mc, z.x, z.y);
     });
 }
 

@@ -1,5 +1,5 @@
 // kernels_ep.cuh — the FFT / external-product kernels (templated on the polynomial size and GLWE dimension):
-// poly_fft_kernel, pbs_kernel, vp_kernel, cmux_tree_kernel.  Instantiated per shape in kernels_n512.cu / kernels_n1024.cu.
+// poly_fft_kernel, pbs_kernel, pbs_wide_kernel, pbs_merged_kernel, vp_kernel, cmux_tree_kernel.  Instantiated per shape in kernels_n512.cu / kernels_n1024.cu.
 #pragma once
 #include <cuda_runtime.h>
 #include "ep_step.cuh"
@@ -487,6 +487,173 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
 template <class C, int NS = 0> struct WideSmem {
     static constexpr size_t bytes = 64 + (size_t)NS * C::G * C::M * sizeof(cplx) + C::acc_words * 8 + (size_t)C::L * C::s_cplx * 16 + (size_t)C::JOBS * C::L * C::M * 4 + (size_t)tab_len(C::N) * 16 + 2 * C::B * sizeof(int) + 16;
 };
+
+// ================================================================================================ PBS, levels merged (throughput path)
+// pbs_kernel runs a step as L × (forward FFT → barrier → MAC → barrier) because one FFT buffer per (ciphertext, polynomial)
+// is all that fits next to the accumulators.  Here the accumulators LEAVE shared memory.  The 16-thread group of job (b, p)
+// is the only writer of accumulator polynomial (b, p) and, apart from the ROTATED reads of the decomposition, its only
+// reader; and each of its threads reads and writes the same 32 coefficients in every step (forward pass 1 consumes samples
+// t + 16m and t + 16m + M, inverse pass B produces exactly those).  So every thread keeps its 32 coefficients in registers,
+// and the copy the rotated reads need lives in the rows of the level-1 FFT buffer, which are dead between the inverse
+// transform of one step and the level-1 forward pass of the next.  Shared memory then holds L buffers per job (184 KB for
+// L = 3, B = 3), the digits of all levels stay in registers (no digit cache), and a step needs TWO CTA barriers:
+//
+//   group (b,p):  rotated reads + digits of all L levels | pass 1 × L | pass 2 × L            ── barrier ──
+//   slot thread:  Σ over all L·G key rows, one prefetch ring                → sums in buffer 1   ── barrier ──
+//   group (b,c):  inverse pass A | pass B + accumulate (registers) + refresh of the rotation copy
+//
+// The long barrier-free stretch lets the warps drift apart, so the shared-memory bursts of one warp overlap the FP64 work of
+// another; the MAC is one contiguous key stream instead of L ramps.  Same arithmetic in the same order as pbs_kernel —
+// bit-identical results (tools/pbs_bench.cu prints the same checksum): 99.8 ms against 111.9 ms for 6144 ciphertexts.
+// BLOG > 0: the decomposition base log as a compile-time constant (shifts and masks fold; 0.6 %).
+template <class C> struct MergedSmem { static constexpr size_t bytes = (size_t)C::L * C::s_cplx * 16 + (size_t)tab_len(C::N) * 16 + 64; };
+
+template <int N, int K, int L, int B, int NT, int MAC_DEPTH = 4, int BLOG = 0>
+__global__ void __launch_bounds__(NT, 1)
+pbs_merged_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
+                  const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
+    typedef EpCfg<N, K, L, B> C;
+    constexpr int JOBS = C::JOBS, ROWS = L * C::G, NMAC = C::M, M = C::M, P = M / 16, SUMS = 1;
+    static_assert(N == 512, "one DFT-16 per thread and pass");
+    static_assert(L >= 2, "the sums use buffer 1, the rotation copy buffer 0");
+    static_assert(NT / 16 >= JOBS && NT >= NMAC && MAC_DEPTH <= ROWS, "thread layout");
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cplx* S = reinterpret_cast<cplx*>(smem_raw);                               // [L][JOBS][M]   (buffer s ↔ level s+1)
+    uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                     // [B][G][N]      rotation copy = buffer 0
+    cplx* wT = S + (size_t)L * C::s_cplx;
+    int* rot_sm = reinterpret_cast<int*>(wT + tab_len(N));                     // [2][B]
+    const int tid = threadIdx.x;
+    const int job = tid >> 4, t = tid & 15;
+    const bool active = job < JOBS;
+    const int ct0 = blockIdx.x * B;
+    const int n1 = n + 1;
+    auto switched = [&](int b, int i) -> int {
+        const int ct = ct0 + b;
+        if (ct >= nct) return 0;
+        uint64_t a = __ldg(lwe_small + (size_t)ct * n1 + i);
+        if (i == n) a += (1ull << 62);
+        return modswitch(a, LogN<N>::v);
+    };
+    for (int i = tid; i < tab_len(N); i += NT) wT[i] = g_wT[i];
+    if (tid < B) { rot_sm[tid] = switched(tid, 0); rot_sm[B + tid] = switched(tid, n); }
+    __syncthreads();
+    for (int idx = tid; idx < (int)C::acc_words; idx += NT) {
+        const int b = idx / (C::G * N), rem = idx - b * C::G * N, p = rem / N, j = rem - p * N;
+        uint64_t v = 0;
+        if (p == K) {
+            const int s = (j + rot_sm[B + b]) & (2 * N - 1);
+            v = (s < N) ? (0ull - alpha) : alpha;
+        }
+        acc[idx] = v;
+    }
+    __syncthreads();
+    uint64_t* Rj = acc + (size_t)(active ? job : 0) * N;                       // this group's polynomial (rotation copy)
+    cplx* Sjob = S + (size_t)(active ? job : 0) * M;                           // + s·JOBS·M for buffer s
+    uint64_t own0[P], own1[P];                                                 // coefficients t + 16m and t + 16m + M
+    static_for<0, P>([&](auto mc) { constexpr int m = decltype(mc)::value; own0[m] = Rj[t + 16 * m]; own1[m] = Rj[t + 16 * m + M]; });
+    const DecompFast dc = make_decomp_fast(BLOG ? BLOG : base_log, L);
+    const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
+    // key row r in MAC order (level L first, polynomial p inside)
+    auto row_ptr = [&](const cplx* ggsw, int r) { return ggsw + (size_t)((L - 1 - r / C::G) * C::G + (r % C::G)) * C::G * C::M; };
+    for (int i = 0; i < n; i++) {
+        const int rot = rot_sm[(i & 1) * B + (active ? job / C::G : 0)];
+        const cplx* ggsw = bsk + ggsw_sz * i;
+        if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+        // ---- digits of all levels: dg[s][m] packs the level-(s+1) digits of samples t+16m (low half) and t+16m+M (high half)
+        uint32_t dg[L][P];
+        if (active) {
+            constexpr int CH = kLoadChunk;
+            constexpr int LOGN = LogN<N>::v;
+            static_for<0, P, CH>([&](auto cc) {
+                constexpr int c0 = decltype(cc)::value;
+                uint64_t v0[CH], v1[CH];
+                uint32_t g0[CH], g1[CH];
+                static_for<0, CH>([&](auto kc) {            // (p · X^rot)[jj], [jj + M]: the loads of a chunk first (rot_diff_pair)
+                    constexpr int k = decltype(kc)::value;
+                    const int jj = t + 16 * (c0 + k);
+                    const uint32_t s0 = (uint32_t)(jj - rot) & (uint32_t)(2 * N - 1);
+                    const uint32_t i0 = s0 & (uint32_t)(N - 1), i1 = i0 ^ (uint32_t)(N / 2);
+                    g0[k] = s0 >> LOGN; g1[k] = g0[k] ^ (i0 >> (LOGN - 1));
+                    v0[k] = Rj[i0]; v1[k] = Rj[i1];
+                });
+                static_for<0, CH>([&](auto kc) {
+                    constexpr int k = decltype(kc)::value, m = c0 + k;
+                    const uint32_t m0 = 0u - g0[k], m1 = 0u - g1[k];
+                    const uint64_t w0 = ((uint64_t)((uint32_t)(v0[k] >> 32) ^ m0) << 32) | ((uint32_t)v0[k] ^ m0);
+                    const uint64_t w1 = ((uint64_t)((uint32_t)(v1[k] >> 32) ^ m1) << 32) | ((uint32_t)v1[k] ^ m1);
+                    uint32_t w[L];
+                    decompose_pair<L>((w0 + g0[k]) - own0[m], (w1 + g1[k]) - own1[m], dc, w);
+                    static_for<0, L>([&](auto sc) { constexpr int s = decltype(sc)::value; dg[s][m] = w[s]; });
+                });
+            });
+        }
+        // ---- forward pass 1 of every level; buffer 0 (the rotation copy) is overwritten last, after the whole group has read it
+        static_for<0, L>([&](auto ic) {
+            constexpr int s = L - 1 - decltype(ic)::value;
+            if (s == 0) __syncwarp();
+            if (active)
+                fft_fwd_pass1_m<N>(t, [&](auto mc, double& a, double& b) { unpack_digits(dg[s][decltype(mc)::value], dc, a, b); },
+                                   Sjob + (size_t)s * JOBS * M);
+        });
+        __syncwarp();
+        // ---- forward pass 2 of every level; then the first key rows are requested (in flight during the barrier)
+        static_for<0, L>([&](auto ic) {
+            constexpr int s = L - 1 - decltype(ic)::value;
+            if (active) fft_fwd_pass2<N>(t, wT, Sjob + (size_t)s * JOBS * M);
+        });
+        cplx g[MAC_DEPTH][C::G];
+        if (tid < NMAC) {
+#pragma unroll
+            for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, NMAC>(row_ptr(ggsw, r), 0, tid, g[r]);
+        }
+        __syncthreads();
+        // ---- Fourier MAC over all L·G key rows; a thread reads and writes only its own slot of every buffer
+        if (tid < NMAC) {
+            cplx out[B][C::G];
+#pragma unroll
+            for (int b = 0; b < B; b++)
+#pragma unroll
+                for (int c = 0; c < C::G; c++) out[b][c] = mk(0.0, 0.0);
+#pragma unroll
+            for (int r = 0; r < ROWS; r++) {
+                const int s = L - 1 - r / C::G, p = r % C::G;
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const cplx x = S[((size_t)s * JOBS + b * C::G + p) * M + tid];
+#pragma unroll
+                    for (int c = 0; c < C::G; c++) cfma(out[b][c], x, g[r % MAC_DEPTH][c]);
+                }
+                if (r + MAC_DEPTH < ROWS) mac_load_row<C, NMAC>(row_ptr(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
+            }
+#pragma unroll
+            for (int b = 0; b < B; b++)
+#pragma unroll
+                for (int c = 0; c < C::G; c++) S[((size_t)SUMS * JOBS + b * C::G + c) * M + tid] = out[b][c];
+        }
+        __syncthreads();
+        // ---- inverse transform of the sums; accumulate in registers; refresh the rotation copy
+        if (active) fft_inv_passA<N>(t, wT, Sjob + (size_t)SUMS * JOBS * M);
+        __syncwarp();
+        if (active)
+            fft_inv_passB_m<N>(t, Sjob + (size_t)SUMS * JOBS * M, [&](auto mc, double re, double im) {
+                constexpr int m = decltype(mc)::value;
+                own0[m] += f64_to_torus(re);
+                own1[m] += f64_to_torus(im);
+                Rj[t + 16 * m] = own0[m];
+                Rj[t + 16 * m + M] = own1[m];
+            });
+        __syncwarp();
+    }
+    __syncthreads();
+    constexpr int LW = K * N + 1;
+    for (int idx = tid; idx < B * LW; idx += NT) {
+        const int b = idx / LW, e = idx - b * LW, ct = ct0 + b;
+        if (ct >= nct) continue;
+        uint64_t v = sample_extract_elem<C>(acc + (size_t)b * C::G * N, e);
+        if (e == K * N) v += alpha;
+        out_big[(size_t)ct * LW + e] = v;
+    }
+}
 
 // ================================================================================================ vertical packing
 // One CTA evaluates B outputs of one box (= one circuit_bootstrap call).  ggsw_f: [nbox][n_in][L][G][G][M].

@@ -41,16 +41,33 @@ cudaError_t launch_pbs_wide(const KLaunch& k, const uint64_t* small, int nct, in
     pbs_wide_kernel<SN, SK, L, 1, 256, DEPTH, NS><<<(unsigned)nct, 256, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
     return cudaGetLastError();
 }
+#if TAC_N == 512
+template <int L, int DEPTH, int BLOG>
+cudaError_t launch_pbs_merged(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
+    typedef EpCfg<SN, SK, L, 3> C;
+    const size_t smem = MergedSmem<C>::bytes;
+    TAC_SET_SMEM((pbs_merged_kernel<SN, SK, L, 3, 256, DEPTH, BLOG>), smem);
+    pbs_merged_kernel<SN, SK, L, 3, 256, DEPTH, BLOG><<<(unsigned)((nct + 2) / 3), 256, smem, k.stream>>>(small, nct, n, bsk, base_log, alpha, k.wT, out);
+    return cudaGetLastError();
+}
+#endif
 template <int L>
 cudaError_t pbs_levels(const KLaunch& k, const uint64_t* small, int nct, int n, const double2* bsk, int base_log, uint64_t alpha, uint64_t* out) {
 #if TAC_N == 512
     // Two kernels, chosen by a wave-count cost model (times of one wave measured on B200, tools/pbs_bench.cu):
-    //  * pbs_kernel, 3 ciphertexts per CTA sharing every BSK load (255 registers, no spills; B = 4 with 320 threads hits a
-    //    168-register cap and is 27 % slower): 8.6 ms per wave of 3·SMs ciphertexts — the throughput configuration;
+    //  * pbs_merged_kernel, 3 ciphertexts per CTA sharing every BSK load, the L levels of a step in one barrier interval
+    //    (255 registers, no spills): 7.1 ms per wave of 3·SMs ciphertexts — the throughput configuration.  (pbs_kernel, the
+    //    level-by-level schedule it replaces, needs 8.0 ms; it remains for level counts whose L buffers do not fit.)
     //  * pbs_wide_kernel, 1 ciphertext per CTA with the levels transformed in parallel: 3.9 ms per wave of SMs ciphertexts
     //    — the latency configuration for small batches (one AES block = 128 ciphertexts).
     const long waves3 = ((nct + 2) / 3 + k.sm_count - 1) / k.sm_count, waves1 = (nct + k.sm_count - 1) / k.sm_count;
-    if (L >= 2 && waves1 * 39 <= waves3 * 86) return launch_pbs_wide<(L >= 2 ? L : 2), 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    if (L >= 2 && waves1 * 39 <= waves3 * 71) return launch_pbs_wide<(L >= 2 ? L : 2), 3>(k, small, nct, n, bsk, base_log, alpha, out);
+    if constexpr (L == 2 || L == 3) {
+        // the shipped base log as a compile-time constant (its shifts and masks fold), any other at run time
+        // (TAC_PBS_GENERIC_BASE_LOG in the environment forces the run-time form: the parity test compares the two)
+        if (base_log == 12 && !getenv("TAC_PBS_GENERIC_BASE_LOG")) return launch_pbs_merged<L, 4, 12>(k, small, nct, n, bsk, base_log, alpha, out);
+        return launch_pbs_merged<L, 4, 0>(k, small, nct, n, bsk, base_log, alpha, out);
+    }
     return launch_pbs<L, 3, 256, 1, 4, 1>(k, small, nct, n, bsk, base_log, alpha, out);      // ring of 4 rows + 1 row staged by cp.async.bulk
 #else
     return launch_pbs<L, 1, 128>(k, small, nct, n, bsk, base_log, alpha, out);      // test-only parameter sets: one instantiation

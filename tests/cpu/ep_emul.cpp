@@ -49,6 +49,45 @@ static void emul_step(const uint64_t* ggsw_std, int base_log, const int* rot, ui
     groups([&](int t, int job) { grp_inv2<C>(t, job, S.data(), acc); });
 }
 
+// one step in the order of pbs_merged_kernel (kernels_ep.cuh): the threads' accumulator coefficients in "registers", the
+// rotation copy aliased onto FFT buffer 0, all levels in one barrier interval.  acc is [B][G][N] as for emul_step.
+template <int N, int K, int L, int B, int NT>
+static void emul_step_merged(const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
+    typedef EpCfg<N, K, L, B> C;
+    constexpr int P = C::M / 16, JOBS = C::JOBS, M = C::M, SUMS = 1, DEPTH = 4;
+    std::vector<cplx> wT(tab_len(N)); build_wT(N, wT.data());
+    const int polys = L * C::G * C::G;
+    std::vector<cplx> gf((size_t)polys * M), kbuf(M);
+    for (int q = 0; q < polys; q++) {
+        for (int t = 0; t < 16; t++) key_fft_pass1<N>(t, ggsw_std + (size_t)q * N, 1.0 / M, kbuf.data());
+        for (int t = 0; t < 16; t++) fft_fwd_pass2<N>(t, wT.data(), kbuf.data());
+        for (int s = 0; s < M; s++) gf[(size_t)q * M + s] = kbuf[s];
+    }
+    std::vector<cplx> S((size_t)L * C::s_cplx);
+    uint64_t* R = reinterpret_cast<uint64_t*>(S.data());                 // buffer 0 doubles as the rotation copy
+    for (size_t i = 0; i < C::acc_words; i++) R[i] = acc[i];
+    struct Regs { uint64_t own0[P], own1[P]; uint32_t dg[L][P]; cplx g[DEPTH][C::G]; };
+    std::vector<Regs> regs(NT);
+    auto groups = [&](auto fn) { for (int tid = 0; tid < NT; tid++) { const int job = tid >> 4, t = tid & 15; if (job < JOBS) fn(tid, t, job); } };
+    groups([&](int tid, int t, int job) { for (int m = 0; m < P; m++) { regs[tid].own0[m] = R[(size_t)job * N + t + 16 * m]; regs[tid].own1[m] = R[(size_t)job * N + t + 16 * m + M]; } });
+    const DecompFast dc = make_decomp_fast(base_log, L);
+    // a group-local __syncwarp() is modelled by finishing a pass for all threads before the next pass starts
+    groups([&](int tid, int t, int job) { mg_digits<C>(t, R + (size_t)job * N, rot[job / C::G], regs[tid].own0, regs[tid].own1, dc, regs[tid].dg); });
+    static_for<0, L>([&](auto ic) {
+        constexpr int s = L - 1 - decltype(ic)::value;
+        groups([&](int tid, int t, int job) {
+            fft_fwd_pass1_m<N>(t, [&](auto mc, double& a, double& b) { unpack_digits(regs[tid].dg[s][decltype(mc)::value], dc, a, b); },
+                               S.data() + ((size_t)s * JOBS + job) * M);
+        });
+    });
+    for (int s = L - 1; s >= 0; s--) groups([&](int, int t, int job) { fft_fwd_pass2<N>(t, wT.data(), S.data() + ((size_t)s * JOBS + job) * M); });
+    for (int tid = 0; tid < M; tid++) mg_mac_prefetch<C, DEPTH>(tid, gf.data(), regs[tid].g);
+    for (int tid = 0; tid < M; tid++) mg_mac<C, DEPTH, SUMS>(tid, gf.data(), S.data(), regs[tid].g);
+    groups([&](int, int t, int job) { fft_inv_passA<N>(t, wT.data(), S.data() + ((size_t)SUMS * JOBS + job) * M); });
+    groups([&](int tid, int t, int job) { mg_inv2<C>(t, S.data() + ((size_t)SUMS * JOBS + job) * M, R + (size_t)job * N, regs[tid].own0, regs[tid].own1); });
+    for (size_t i = 0; i < C::acc_words; i++) acc[i] = R[i];
+}
+
 // forward transform of a real polynomial given as doubles; returns slot-ordered spectrum + the frequency held by each slot
 template <int N>
 static void emul_fft(const double* in, double* out_re, double* out_im, int* slot_freq) {
@@ -73,8 +112,14 @@ template <int L> static void digits_t(uint64_t x, int b, double* out) {
 extern "C" {
 int emul_cmux_step(int N, int K, int L, int B, int NT, const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
 #define CASE(n, k, l, b, nt) if (N == n && K == k && L == l && B == b && NT == nt) { emul_step<n, k, l, b, nt>(ggsw_std, base_log, rot, acc); return 0; }
-    CASE(512, 4, 3, 3, 256) CASE(512, 4, 3, 4, 320) CASE(512, 4, 3, 2, 256) CASE(512, 4, 1, 3, 256) CASE(512, 4, 1, 4, 320) CASE(512, 4, 1, 1, 256)
+    CASE(512, 4, 3, 3, 256) CASE(512, 4, 2, 3, 256) CASE(512, 4, 3, 4, 320) CASE(512, 4, 3, 2, 256) CASE(512, 4, 1, 3, 256) CASE(512, 4, 1, 4, 320) CASE(512, 4, 1, 1, 256)
     CASE(1024, 2, 2, 2, 256) CASE(1024, 2, 4, 2, 256) CASE(1024, 2, 1, 2, 256) CASE(1024, 2, 1, 1, 96)
+#undef CASE
+    return -1;
+}
+int emul_cmux_step_merged(int N, int K, int L, int B, int NT, const uint64_t* ggsw_std, int base_log, const int* rot, uint64_t* acc) {
+#define CASE(n, k, l, b, nt) if (N == n && K == k && L == l && B == b && NT == nt) { emul_step_merged<n, k, l, b, nt>(ggsw_std, base_log, rot, acc); return 0; }
+    CASE(512, 4, 3, 3, 256) CASE(512, 4, 2, 3, 256)
 #undef CASE
     return -1;
 }

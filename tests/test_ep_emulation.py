@@ -20,6 +20,7 @@ def emul():
     up = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
     E.emul_fft_fwd_inv.argtypes = [C.c_int, dp, dp, dp, ip]
     E.emul_cmux_step.argtypes = [C.c_int] * 5 + [up, C.c_int, ip, up]
+    E.emul_cmux_step_merged.argtypes = [C.c_int] * 5 + [up, C.c_int, ip, up]
     E.emul_digits.argtypes = [C.c_uint64, C.c_int, C.c_int, dp]
     E.emul_f64_to_torus.restype = C.c_uint64
     E.emul_f64_to_torus.argtypes = [C.c_double]
@@ -105,6 +106,29 @@ def test_cmux_step_matches_oracle(emul, ol, oracle64, case):
     diff = np.abs((got - want).astype(np.int64)).astype(np.float64)
     # f64 rounding tolerance: both sides are unnormalised f64 FFTs in different operation order; |x| <= 2^23 ⇒ 2^-30 abs
     assert diff.max() < 2.0**35, np.log2(diff.max())
+
+
+@pytest.mark.parametrize("L,blog", [(3, 12), (2, 15)])
+def test_merged_step_equals_level_by_level_step(emul, ol, oracle64, L, blog):
+    """pbs_merged_kernel's schedule (accumulator coefficients in registers, rotation copy aliased onto FFT buffer 0, all levels in
+    one barrier interval) performs the same arithmetic in the same order as the level-by-level step: the SAME words, two steps
+    in a row (the second consumes the refreshed rotation copy)."""
+    N, K, B, NT = 512, 4, 3, 256
+    G = K + 1
+    rng = np.random.default_rng(100 + L)
+    if L == 3:
+        ggsws = [np.ascontiguousarray(oracle64.bsk.reshape(oracle64.p.n, L, G, G, N)[i]) for i in (11, 12)]
+    else:
+        ggsws = [rng.integers(0, 2**64, (L, G, G, N), dtype=np.uint64) for _ in range(2)]
+    acc = rng.integers(0, 2**64, (B, G, N), dtype=np.uint64)
+    a, b = acc.copy(), acc.copy()
+    for step, ggsw in enumerate(ggsws):
+        rot = rng.integers(0, 2 * N, B).astype(np.int32)
+        rot[step] = (0, 2 * N - 1)[step]
+        assert emul.emul_cmux_step(N, K, L, B, NT, ggsw, blog, rot, a) == 0
+        assert emul.emul_cmux_step_merged(N, K, L, B, NT, ggsw, blog, rot, b) == 0
+        assert np.array_equal(a, b), f"step {step}"
+    assert not np.array_equal(a, acc)
 
 
 _plans = {}

@@ -332,7 +332,7 @@ TAC_HD void fft_fwd_pass2(int t, const cplx* __restrict__ wT, const cplx (&tw)[F
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass A (in place)
 // the 16 twiddles are requested together with the data, ahead of the arithmetic (same reasoning as above)
-template <int N>
+template <int N, int MODE = (TAC_TW_DERIVE ? 2 : TAC_INV_TW_EARLY ? 1 : 0)>
 TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__ S) {
     constexpr int M = N / 2, P = M / 16;
 #pragma unroll
@@ -340,7 +340,7 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
         const int q = t + 16 * c2;
         cplx v[16];
         static_for<0, 16>([&](auto rc) { constexpr int r = decltype(rc)::value; v[bitrev<16>(r)] = S[slot_of(q, r)]; });
-#if TAC_TW_DERIVE
+        if constexpr (MODE == 2) {
         // ρ_q^t for t = 1, 2, 4, 8 from the table, the other powers as products (at most three multiplications deep)
         cplx w[16];
         w[1] = wT[slot_of(q, 1)]; w[2] = wT[slot_of(q, 2)]; w[4] = wT[slot_of(q, 4)]; w[8] = wT[slot_of(q, 8)];
@@ -349,16 +349,16 @@ TAC_HD void fft_inv_passA(int t, const cplx* __restrict__ wT, cplx* __restrict__
         static_for<9, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; w[tt] = cmul(w[8], w[tt - 8]); });
         S[slot_of(q, 0)] = v[0];
         static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; S[slot_of(q, tt)] = cmul_conj(v[tt], w[tt]); });
-#elif TAC_INV_TW_EARLY
+        } else if constexpr (MODE == 1) {
         cplx w[16];
         static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; w[tt] = wT[slot_of(q, tt)]; });
         dft_inv<16>(v);
         S[slot_of(q, 0)] = v[0];
         static_for<1, 16>([&](auto tc) { constexpr int tt = decltype(tc)::value; S[slot_of(q, tt)] = cmul_conj(v[tt], w[tt]); });
-#else
+        } else {
         dft_inv<16>(v);
         twiddle_store_conj<16>(v, [&](int tt) { return slot_of(q, tt); }, wT, S);
-#endif
+        }
     }
 }
 // ------------------------------------------------------------------------------------------------ inverse, pass B

@@ -18,6 +18,7 @@
 //   group:  fwd1(l) | fwd2                 ── barrier ──  all: mac(l)     ── barrier ──      l = L-1 … 1   (mac(1) also writes out)
 //   group:  inv1 | inv2 |                                                                     ( | = __syncwarp )
 // Both the CUDA kernels (kernels_ep.cuh) and the CPU emulation (tests/cpu/ep_emul.cpp) follow this order.
+// pbs_merged_kernel runs the L levels of a step in ONE barrier interval (accumulators in registers): see the mg_* functions.
 #pragma once
 #include "ep_core.cuh"
 
@@ -198,6 +199,86 @@ TAC_HD void grp_inv2(int t, int job, const cplx* __restrict__ S, uint64_t* __res
     fft_inv_passB<C::N>(t, S + (size_t)job * C::M, [&](int jj, double re, double im) {
         poly[jj] += f64_to_torus(re);
         poly[jj + C::M] += f64_to_torus(im);
+    });
+}
+
+// ------------------------------------------------------------------------------------------------ levels-merged step (pbs_merged_kernel)
+// Phase functions of the schedule that keeps the accumulator coefficients of a thread in registers (own0[m], own1[m]:
+// coefficients t + 16m and t + 16m + M of the group's polynomial) and the rotation copy `Rj` in the rows of FFT buffer 0.
+//
+// digits of all L levels of (Rj · X^rot − own): dg[s][m] packs the level-(s+1) digits of samples t + 16m (low half-word) and
+// t + 16m + M (high half-word); the rotated loads of a chunk are issued first (cf. rot_diff_pair)
+template <class C>
+TAC_HD void mg_digits(int t, const uint64_t* __restrict__ Rj, int rot, const uint64_t (&own0)[C::M / 16], const uint64_t (&own1)[C::M / 16],
+                      const DecompFast& dc, uint32_t (&dg)[C::L][C::M / 16]) {
+    constexpr int N = C::N, P = C::M / 16, CH = kLoadChunk;
+    constexpr int LOGN = (N == 256) ? 8 : (N == 512) ? 9 : (N == 1024) ? 10 : 11;
+    static_for<0, P, CH>([&](auto cc) {
+        constexpr int c0 = decltype(cc)::value;
+        uint64_t v0[CH], v1[CH];
+        uint32_t g0[CH], g1[CH];
+        static_for<0, CH>([&](auto kc) {
+            constexpr int k = decltype(kc)::value;
+            const int jj = t + 16 * (c0 + k);
+            const uint32_t s0 = (uint32_t)(jj - rot) & (uint32_t)(2 * N - 1);
+            const uint32_t i0 = s0 & (uint32_t)(N - 1), i1 = i0 ^ (uint32_t)(N / 2);
+            g0[k] = s0 >> LOGN; g1[k] = g0[k] ^ (i0 >> (LOGN - 1));
+            v0[k] = Rj[i0]; v1[k] = Rj[i1];
+        });
+        static_for<0, CH>([&](auto kc) {
+            constexpr int k = decltype(kc)::value, m = c0 + k;
+            const uint32_t m0 = 0u - g0[k], m1 = 0u - g1[k];
+            const uint64_t w0 = ((uint64_t)((uint32_t)(v0[k] >> 32) ^ m0) << 32) | ((uint32_t)v0[k] ^ m0);
+            const uint64_t w1 = ((uint64_t)((uint32_t)(v1[k] >> 32) ^ m1) << 32) | ((uint32_t)v1[k] ^ m1);
+            uint32_t w[C::L];
+            decompose_pair<C::L>((w0 + g0[k]) - own0[m], (w1 + g1[k]) - own1[m], dc, w);
+            static_for<0, C::L>([&](auto sc) { constexpr int s = decltype(sc)::value; dg[s][m] = w[s]; });
+        });
+    });
+}
+// key row r of a step's Fourier GGSW in MAC order: level L first, polynomial p inside
+template <class C>
+TAC_HD const cplx* mg_row(const cplx* __restrict__ ggsw, int r) { return ggsw + (size_t)((C::L - 1 - r / C::G) * C::G + (r % C::G)) * C::G * C::M; }
+template <class C, int MAC_DEPTH>
+TAC_HD void mg_mac_prefetch(int tid, const cplx* __restrict__ ggsw, cplx (&g)[MAC_DEPTH][C::G]) {
+#pragma unroll
+    for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, C::M>(mg_row<C>(ggsw, r), 0, tid, g[r]);
+}
+// slot thread `tid`: Σ over all L·G key rows of the spectra in S[L][JOBS][M] (buffer s ↔ level s+1); the sums replace the
+// thread's own slot of buffer `SUMS` (a thread reads and writes only its own slot of every buffer)
+template <class C, int MAC_DEPTH, int SUMS>
+TAC_HD void mg_mac(int tid, const cplx* __restrict__ ggsw, cplx* __restrict__ S, cplx (&g)[MAC_DEPTH][C::G]) {
+    constexpr int ROWS = C::L * C::G;
+    cplx out[C::B][C::G];
+#pragma unroll
+    for (int b = 0; b < C::B; b++)
+#pragma unroll
+        for (int c = 0; c < C::G; c++) out[b][c] = mk(0.0, 0.0);
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+        const int s = C::L - 1 - r / C::G, p = r % C::G;
+#pragma unroll
+        for (int b = 0; b < C::B; b++) {
+            const cplx x = S[((size_t)s * C::JOBS + b * C::G + p) * C::M + tid];
+#pragma unroll
+            for (int c = 0; c < C::G; c++) cfma(out[b][c], x, g[r % MAC_DEPTH][c]);
+        }
+        if (r + MAC_DEPTH < ROWS) mac_load_row<C, C::M>(mg_row<C>(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
+    }
+#pragma unroll
+    for (int b = 0; b < C::B; b++)
+#pragma unroll
+        for (int c = 0; c < C::G; c++) S[((size_t)SUMS * C::JOBS + b * C::G + c) * C::M + tid] = out[b][c];
+}
+// inverse pass B of the sums + accumulate into the thread's coefficients + refresh of the rotation copy
+template <class C>
+TAC_HD void mg_inv2(int t, const cplx* __restrict__ Ssum, uint64_t* __restrict__ Rj, uint64_t (&own0)[C::M / 16], uint64_t (&own1)[C::M / 16]) {
+    fft_inv_passB_m<C::N>(t, Ssum, [&](auto mc, double re, double im) {
+        constexpr int m = decltype(mc)::value;
+        own0[m] += f64_to_torus(re);
+        own1[m] += f64_to_torus(im);
+        Rj[t + 16 * m] = own0[m];
+        Rj[t + 16 * m + C::M] = own1[m];
     });
 }
 

@@ -513,10 +513,10 @@ __global__ void __launch_bounds__(NT, 1)
 pbs_merged_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cplx* __restrict__ bsk, int base_log, uint64_t alpha,
                   const cplx* __restrict__ g_wT, uint64_t* __restrict__ out_big) {
     typedef EpCfg<N, K, L, B> C;
-    constexpr int JOBS = C::JOBS, ROWS = L * C::G, NMAC = C::M, M = C::M, P = M / 16, SUMS = 1;
+    constexpr int JOBS = C::JOBS, NMAC = C::M, M = C::M, P = M / 16, SUMS = 1;
     static_assert(N == 512, "one DFT-16 per thread and pass");
     static_assert(L >= 2, "the sums use buffer 1, the rotation copy buffer 0");
-    static_assert(NT / 16 >= JOBS && NT >= NMAC && MAC_DEPTH <= ROWS, "thread layout");
+    static_assert(NT / 16 >= JOBS && NT >= NMAC && MAC_DEPTH <= L * C::G, "thread layout");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cplx* S = reinterpret_cast<cplx*>(smem_raw);                               // [L][JOBS][M]   (buffer s ↔ level s+1)
     uint64_t* acc = reinterpret_cast<uint64_t*>(smem_raw);                     // [B][G][N]      rotation copy = buffer 0
@@ -553,40 +553,13 @@ pbs_merged_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const 
     static_for<0, P>([&](auto mc) { constexpr int m = decltype(mc)::value; own0[m] = Rj[t + 16 * m]; own1[m] = Rj[t + 16 * m + M]; });
     const DecompFast dc = make_decomp_fast(BLOG ? BLOG : base_log, L);
     const size_t ggsw_sz = (size_t)L * C::G * C::G * C::M;
-    // key row r in MAC order (level L first, polynomial p inside)
-    auto row_ptr = [&](const cplx* ggsw, int r) { return ggsw + (size_t)((L - 1 - r / C::G) * C::G + (r % C::G)) * C::G * C::M; };
     for (int i = 0; i < n; i++) {
         const int rot = rot_sm[(i & 1) * B + (active ? job / C::G : 0)];
         const cplx* ggsw = bsk + ggsw_sz * i;
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
-        // ---- digits of all levels: dg[s][m] packs the level-(s+1) digits of samples t+16m (low half) and t+16m+M (high half)
+        // ---- digits of all levels, in registers
         uint32_t dg[L][P];
-        if (active) {
-            constexpr int CH = kLoadChunk;
-            constexpr int LOGN = LogN<N>::v;
-            static_for<0, P, CH>([&](auto cc) {
-                constexpr int c0 = decltype(cc)::value;
-                uint64_t v0[CH], v1[CH];
-                uint32_t g0[CH], g1[CH];
-                static_for<0, CH>([&](auto kc) {            // (p · X^rot)[jj], [jj + M]: the loads of a chunk first (rot_diff_pair)
-                    constexpr int k = decltype(kc)::value;
-                    const int jj = t + 16 * (c0 + k);
-                    const uint32_t s0 = (uint32_t)(jj - rot) & (uint32_t)(2 * N - 1);
-                    const uint32_t i0 = s0 & (uint32_t)(N - 1), i1 = i0 ^ (uint32_t)(N / 2);
-                    g0[k] = s0 >> LOGN; g1[k] = g0[k] ^ (i0 >> (LOGN - 1));
-                    v0[k] = Rj[i0]; v1[k] = Rj[i1];
-                });
-                static_for<0, CH>([&](auto kc) {
-                    constexpr int k = decltype(kc)::value, m = c0 + k;
-                    const uint32_t m0 = 0u - g0[k], m1 = 0u - g1[k];
-                    const uint64_t w0 = ((uint64_t)((uint32_t)(v0[k] >> 32) ^ m0) << 32) | ((uint32_t)v0[k] ^ m0);
-                    const uint64_t w1 = ((uint64_t)((uint32_t)(v1[k] >> 32) ^ m1) << 32) | ((uint32_t)v1[k] ^ m1);
-                    uint32_t w[L];
-                    decompose_pair<L>((w0 + g0[k]) - own0[m], (w1 + g1[k]) - own1[m], dc, w);
-                    static_for<0, L>([&](auto sc) { constexpr int s = decltype(sc)::value; dg[s][m] = w[s]; });
-                });
-            });
-        }
+        if (active) mg_digits<C>(t, Rj, rot, own0, own1, dc, dg);
         // ---- forward pass 1 of every level; buffer 0 (the rotation copy) is overwritten last, after the whole group has read it
         static_for<0, L>([&](auto ic) {
             constexpr int s = L - 1 - decltype(ic)::value;
@@ -602,46 +575,15 @@ pbs_merged_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const 
             if (active) fft_fwd_pass2<N>(t, wT, Sjob + (size_t)s * JOBS * M);
         });
         cplx g[MAC_DEPTH][C::G];
-        if (tid < NMAC) {
-#pragma unroll
-            for (int r = 0; r < MAC_DEPTH; r++) mac_load_row<C, NMAC>(row_ptr(ggsw, r), 0, tid, g[r]);
-        }
+        if (tid < NMAC) mg_mac_prefetch<C, MAC_DEPTH>(tid, ggsw, g);
         __syncthreads();
         // ---- Fourier MAC over all L·G key rows; a thread reads and writes only its own slot of every buffer
-        if (tid < NMAC) {
-            cplx out[B][C::G];
-#pragma unroll
-            for (int b = 0; b < B; b++)
-#pragma unroll
-                for (int c = 0; c < C::G; c++) out[b][c] = mk(0.0, 0.0);
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) {
-                const int s = L - 1 - r / C::G, p = r % C::G;
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const cplx x = S[((size_t)s * JOBS + b * C::G + p) * M + tid];
-#pragma unroll
-                    for (int c = 0; c < C::G; c++) cfma(out[b][c], x, g[r % MAC_DEPTH][c]);
-                }
-                if (r + MAC_DEPTH < ROWS) mac_load_row<C, NMAC>(row_ptr(ggsw, r + MAC_DEPTH), 0, tid, g[r % MAC_DEPTH]);
-            }
-#pragma unroll
-            for (int b = 0; b < B; b++)
-#pragma unroll
-                for (int c = 0; c < C::G; c++) S[((size_t)SUMS * JOBS + b * C::G + c) * M + tid] = out[b][c];
-        }
+        if (tid < NMAC) mg_mac<C, MAC_DEPTH, SUMS>(tid, ggsw, S, g);
         __syncthreads();
         // ---- inverse transform of the sums; accumulate in registers; refresh the rotation copy
         if (active) fft_inv_passA<N>(t, wT, Sjob + (size_t)SUMS * JOBS * M);
         __syncwarp();
-        if (active)
-            fft_inv_passB_m<N>(t, Sjob + (size_t)SUMS * JOBS * M, [&](auto mc, double re, double im) {
-                constexpr int m = decltype(mc)::value;
-                own0[m] += f64_to_torus(re);
-                own1[m] += f64_to_torus(im);
-                Rj[t + 16 * m] = own0[m];
-                Rj[t + 16 * m + M] = own1[m];
-            });
+        if (active) mg_inv2<C>(t, Sjob + (size_t)SUMS * JOBS * M, Rj, own0, own1);
         __syncwarp();
     }
     __syncthreads();

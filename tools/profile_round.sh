@@ -25,4 +25,6 @@ timeout 900 ncu --set full --clock-control none --import-source on --launch-skip
 tail -3 gpurun_out/ncu_full_$TAG.log
 # condensed evidence next to the report; KEEP_REP=0 drops the (≈ 40 MB) report itself — gpurun copies back at most 64 MiB
 python tools/ncu_summary.py gpurun_out/prof_round_$TAG.ncu-rep gpurun_out/round_$TAG > /dev/null
+# PHASE_KERNEL=regex: stall samples per barrier-delimited phase of that kernel (tools/ncu_phase_table.py)
+if [ -n "$PHASE_KERNEL" ]; then python tools/ncu_phase_table.py gpurun_out/prof_round_$TAG.ncu-rep "$PHASE_KERNEL" > gpurun_out/phases_$TAG.md 2>&1; fi
 if [ "${KEEP_REP:-1}" = "0" ]; then rm -f gpurun_out/prof_round_$TAG.ncu-rep; fi

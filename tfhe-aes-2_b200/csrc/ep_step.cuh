@@ -208,6 +208,10 @@ TAC_HD void grp_inv2(int t, int job, const cplx* __restrict__ S, uint64_t* __res
 //
 // digits of all L levels of (Rj · X^rot − own): dg[s][m] packs the level-(s+1) digits of samples t + 16m (low half-word) and
 // t + 16m + M (high half-word); the rotated loads of a chunk are issued first (cf. rot_diff_pair)
+// TAC_MG_TIE_CHUNK = 0: one tie test per coefficient pair (decompose_pair), the form the other kernels use — 1.7 % slower here
+#ifndef TAC_MG_TIE_CHUNK
+#define TAC_MG_TIE_CHUNK 1
+#endif
 template <class C>
 TAC_HD void mg_digits(int t, const uint64_t* __restrict__ Rj, int rot, const uint64_t (&own0)[C::M / 16], const uint64_t (&own1)[C::M / 16],
                       const DecompFast& dc, uint32_t (&dg)[C::L][C::M / 16]) {
@@ -225,6 +229,41 @@ TAC_HD void mg_digits(int t, const uint64_t* __restrict__ Rj, int rot, const uin
             g0[k] = s0 >> LOGN; g1[k] = g0[k] ^ (i0 >> (LOGN - 1));
             v0[k] = Rj[i0]; v1[k] = Rj[i1];
         });
+#if TAC_MG_TIE_CHUNK
+        // closed-form digits of the whole chunk, ONE tie test per chunk (a branch per pair exposes the latency of the
+        // pair's dependent chain every time: in-order issue waits for the predicate)
+        uint64_t x0[CH], x1[CH];
+        uint32_t probe = 0;
+        static_for<0, CH>([&](auto kc) {
+            constexpr int k = decltype(kc)::value, m = c0 + k;
+            const uint32_t m0 = 0u - g0[k], m1 = 0u - g1[k];
+            const uint64_t w0 = ((uint64_t)((uint32_t)(v0[k] >> 32) ^ m0) << 32) | ((uint32_t)v0[k] ^ m0);
+            const uint64_t w1 = ((uint64_t)((uint32_t)(v1[k] >> 32) ^ m1) << 32) | ((uint32_t)v1[k] ^ m1);
+            x0[k] = (w0 + g0[k]) - own0[m]; x1[k] = (w1 + g1[k]) - own1[m];
+            const uint64_t y0 = x0[k] + dc.add, y1 = x1[k] + dc.add;
+            static_for<0, C::L>([&](auto sc) {
+                constexpr int s = decltype(sc)::value, l = s + 1;
+                const uint32_t f0 = (uint32_t)(y0 >> (64 - dc.b * l)) & dc.mask;
+                const uint32_t f1 = (uint32_t)(y1 >> (64 - dc.b * l)) & dc.mask;
+                dg[s][m] = f0 | (f1 << 16);
+                probe |= dg[s][m] - 0x00010001u;
+            });
+        });
+        if (probe & 0x80008000u) {                       // some pair of the chunk may hold an exact tie: replay those exactly
+            static_for<0, CH>([&](auto kc) {
+                constexpr int k = decltype(kc)::value, m = c0 + k;
+                uint32_t pm = 0;
+                static_for<0, C::L>([&](auto sc) { pm |= dg[decltype(sc)::value][m] - 0x00010001u; });
+                if (pm & 0x80008000u) {
+                    const uint64_t p0 = decompose_digits_slow<C::L>(x0[k], dc.b), p1 = decompose_digits_slow<C::L>(x1[k], dc.b);
+                    static_for<0, C::L>([&](auto sc) {
+                        constexpr int s = decltype(sc)::value;
+                        dg[s][m] = ((uint32_t)(p0 >> (16 * s)) & 0xFFFFu) | (((uint32_t)(p1 >> (16 * s)) & 0xFFFFu) << 16);
+                    });
+                }
+            });
+        }
+#else
         static_for<0, CH>([&](auto kc) {
             constexpr int k = decltype(kc)::value, m = c0 + k;
             const uint32_t m0 = 0u - g0[k], m1 = 0u - g1[k];
@@ -234,6 +273,7 @@ TAC_HD void mg_digits(int t, const uint64_t* __restrict__ Rj, int rot, const uin
             decompose_pair<C::L>((w0 + g0[k]) - own0[m], (w1 + g1[k]) - own1[m], dc, w);
             static_for<0, C::L>([&](auto sc) { constexpr int s = decltype(sc)::value; dg[s][m] = w[s]; });
         });
+#endif
     });
 }
 // key row r of a step's Fourier GGSW in MAC order: level L first, polynomial p inside

@@ -504,7 +504,7 @@ template <class C, int NS = 0> struct WideSmem {
 //
 // The long barrier-free stretch lets the warps drift apart, so the shared-memory bursts of one warp overlap the FP64 work of
 // another; the MAC is one contiguous key stream instead of L ramps.  Same arithmetic in the same order as pbs_kernel —
-// bit-identical results (tools/pbs_bench.cu prints the same checksum): 99.8 ms against 111.9 ms for 6144 ciphertexts.
+// bit-identical results (tools/pbs_bench.cu prints the same checksum): 98.3 ms against 111.9 ms for 6144 ciphertexts.
 // BLOG > 0: the decomposition base log as a compile-time constant (shifts and masks fold; 0.6 %).
 template <class C> struct MergedSmem { static constexpr size_t bytes = (size_t)C::L * C::s_cplx * 16 + (size_t)tab_len(C::N) * 16 + 64; };
 

@@ -15,6 +15,7 @@
 #include "experiments/kernels_park.cuh"
 #include "experiments/kernels_wide512.cuh"
 #include "experiments/kernels_merged.cuh"
+#include "experiments/kernels_wide_tma.cuh"
 
 using namespace tac;
 
@@ -249,6 +250,36 @@ void run_merged_prod(const char* name, const Bufs& b) {
     fflush(stdout);
 }
 
+template <int R, int NT_>
+void run_wide_tma(const char* name, const Bufs& b) {
+    typedef EpCfg<N, K, L, 1> C;
+    const size_t smem = WideTmaSmem<C, R>::bytes;
+    auto kern = pbs_wide_tma_kernel<N, K, L, NT_, R>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaFuncAttributes fa; CK(cudaFuncGetAttributes(&fa, kern));
+    int occ = 0; CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, NT_, smem));
+    cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaMemset(b.out, 0, (size_t)b.nct * (K * N + 1) * 8));
+    kern<<<b.nct, NT_, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f, tot = 0;
+    for (int r = 0; r < b.reps; r++) {
+        CK(cudaEventRecord(e0));
+        kern<<<b.nct, NT_, smem>>>(b.small, b.nct, n_lwe, b.bsk, BASE_LOG, 1ull << 50, b.wT, b.out);
+        CK(cudaEventRecord(e1));
+        CK(cudaEventSynchronize(e1));
+        float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+        best = ms < best ? ms : best; tot += ms;
+    }
+    CK(cudaMemset(b.sum, 0, 8));
+    checksum_kernel<<<256, 256>>>(b.out, (size_t)b.nct * (K * N + 1), b.sum);
+    unsigned long long h; CK(cudaMemcpy(&h, b.sum, 8, cudaMemcpyDeviceToHost));
+    const double flop = (double)b.nct * n_lwe * 389120.0;
+    printf("%-28s regs=%3d lmem=%4zu smem=%6zu occ=%d  best %8.3f ms  avg %8.3f ms  %6.2f TF/s  frac %.3f  %7.1f PBS/ms  sum=%016llx\n", name, fa.numRegs,
+           (size_t)fa.localSizeBytes, smem, occ, best, tot / b.reps, flop / (best * 1e-3) / 1e12, flop / (best * 1e-3) / 1e12 / b.peak, b.nct / best, h);
+    fflush(stdout);
+}
+
 int main(int argc, char** argv) {
     Bufs b;
     b.nct = argc > 1 ? atoi(argv[1]) : 6144;
@@ -289,6 +320,7 @@ int main(int argc, char** argv) {
 #define VP(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, false>("park B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #define VM(B_, NT_, D_, NS_) if (mask & (1u << v)) run_merged<B_, NT_, D_, NS_>("merged B=" #B_ " depth=" #D_ " staged=" #NS_, b); v++;
 #define VMP(B_, NT_, D_, BL_) if (mask & (1u << v)) run_merged_prod<B_, NT_, D_, BL_>("merged(prod) B=" #B_ " depth=" #D_ " blog=" #BL_, b); v++;
+#define VWT(R_, NT_) if (mask & (1u << v)) run_wide_tma<R_, NT_>("wide/tma ring=" #R_ " NT=" #NT_, b); v++;
 #define VW5(D_) if (mask & (1u << v)) run_wide512<D_>("wide512 depth=" #D_, b); v++;
 #define VS(B_, NT_, D_) if (mask & (1u << v)) run_park<B_, NT_, D_, true>("park/split B=" #B_ " NT=" #NT_ " depth=" #D_, b); v++;
 #ifndef TAC_VARIANTS
@@ -302,6 +334,7 @@ int main(int argc, char** argv) {
 #undef VP
 #undef VS
 #undef VW5
+#undef VWT
 #undef VMP
 #undef VM
     return 0;

@@ -202,7 +202,7 @@ PBS_SOURCES = ("tac_common.h", "ep_core.cuh", "ep_step.cuh", "kernels_ep.cuh", "
 
 
 def csrc_digest():
-    """sha256 over the sources `pbs_kernel` is compiled from: ties a committed ncu capture to the code it profiled (the GPU box
+    """sha256 over the sources the PBS kernels are compiled from: ties a committed ncu capture to the code it profiled (the GPU box
     has no .git, so a commit hash cannot be checked there)"""
     import hashlib
     h = hashlib.sha256()
@@ -213,7 +213,7 @@ def csrc_digest():
 
 
 def pbs_traffic(n_ct):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one pbs_kernel launch from the committed `ncu --set full` capture
+    """dram__bytes_read.sum + dram__bytes_write.sum of one PBS launch (`pbs_merged_kernel`) from the committed `ncu --set full` capture
     (profiles/pbs_dram_traffic.json), but only when that capture profiled exactly the kernel sources of this tree; otherwise None."""
     try:
         table = json.load(open(os.path.join(ROOT, "profiles", "pbs_dram_traffic.json")))

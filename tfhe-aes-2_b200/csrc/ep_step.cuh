@@ -202,6 +202,24 @@ TAC_HD void grp_inv2(int t, int job, const cplx* __restrict__ S, uint64_t* __res
     });
 }
 
+// ------------------------------------------------------------------------------------------------ L2 prefetch of the key stream
+// The CTAs of a launch walk the bootstrapping key in step, and the 208 MB key does not fit L2: it streams from HBM once per
+// wave, and whichever CTA reaches GGSW i first waits for HBM inside its MAC (then every CTA of the wave waits with it on the
+// same lines).  So every CTA asks L2 for a slice of the GGSW of a LATER step while it works on the current one: `slices` CTAs
+// (consecutive block indices are co-resident) cover the GGSW between them, one 128-byte line per thread.  Measured on B200:
+// blind rotation of 16384 ciphertexts 260.3 → 253.9 ms, of 6144 98.3 → 95.9 ms (distance 1, 2 and 4 steps alike).
+#if defined(__CUDACC__)
+template <class C>
+__device__ __forceinline__ void ggsw_l2_prefetch(const cplx* __restrict__ ggsw, int tid, int nthreads) {
+    constexpr int LINES = (int)((size_t)C::L * C::G * C::G * C::M * sizeof(cplx) / 128);
+    const int slices = min((int)gridDim.x, 128);
+    const int per = min((LINES + slices - 1) / slices, nthreads);
+    const int line = (int)(blockIdx.x % slices) * per + tid;
+    if (tid < per && line < LINES) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(ggsw) + (size_t)line * 128));
+}
+#endif
+constexpr int kL2PrefetchSteps = 2;          // how many steps ahead
+
 // ------------------------------------------------------------------------------------------------ levels-merged step (pbs_merged_kernel)
 // Phase functions of the schedule that keeps the accumulator coefficients of a thread in registers (own0[m], own1[m]:
 // coefficients t + 16m and t + 16m + M of the group's polynomial) and the rotation copy `Rj` in the rows of FFT buffer 0.

@@ -380,6 +380,9 @@ pbs_wide_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const cp
         const cplx* ggsw = bsk + ggsw_sz * i;
 #endif
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+#ifndef TAC_DBG_KEY_ONE_ROW
+        if (i + kL2PrefetchSteps < n) ggsw_l2_prefetch<C>(ggsw + ggsw_sz * kL2PrefetchSteps, tid, NT);
+#endif
         if (NS > 0 && tid == 0) {              // rows ROWS-NS … ROWS-1 of this step: in flight during P0 and P1
             kstage::mbar_expect_tx(kbar, NS * ROW_BYTES);
 #pragma unroll
@@ -557,6 +560,7 @@ pbs_merged_kernel(const uint64_t* __restrict__ lwe_small, int nct, int n, const 
         const int rot = rot_sm[(i & 1) * B + (active ? job / C::G : 0)];
         const cplx* ggsw = bsk + ggsw_sz * i;
         if (tid < B && i + 1 < n) rot_sm[((i + 1) & 1) * B + tid] = switched(tid, i + 1);      // consumed after >= 1 barrier
+        if (i + kL2PrefetchSteps < n) ggsw_l2_prefetch<C>(ggsw + ggsw_sz * kL2PrefetchSteps, tid, NT);
         // ---- digits of all levels, in registers
         uint32_t dg[L][P];
         if (active) mg_digits<C>(t, Rj, rot, own0, own1, dc, dg);
